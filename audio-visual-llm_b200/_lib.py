@@ -1,0 +1,193 @@
+"""ctypes binding of libavconnector_b200.so (the C ABI in include/avconnector_b200.h).
+
+This is the only way the host layer reaches the GPU kernels.  There is no fallback: if the library is
+missing or the device is not sm_100 every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libavconnector_b200.so"
+_lib: Optional[C.CDLL] = None
+
+AVC_ABI_VERSION = 1
+EXPORTS = (
+    "avc_abi_version", "avc_last_error", "avc_device_check", "avc_gather_fwd", "avc_proj_fwd",
+    "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",
+    "avc_splice_bwd",
+)
+
+
+class AvcFeat(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p), ("batch_stride", C.c_int64), ("frame_stride", C.c_int64),
+        ("frames", C.c_int32), ("dim", C.c_int32), ("stack", C.c_int32), ("reserved", C.c_int32),
+        ("valid_frames", C.c_void_p),
+    ]
+
+
+class AvcMat(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("row_stride", C.c_int64),
+        ("batches", C.c_int64), ("batch_stride", C.c_int64),
+    ]
+
+
+class AvcSplice(C.Structure):
+    _fields_ = [
+        ("input_ids", C.c_void_p), ("placeholder_id", C.c_int64), ("pad_id", C.c_int64),
+        ("batch", C.c_int32), ("seq", C.c_int32), ("hidden", C.c_int32), ("tokens_per_sample", C.c_int32),
+        ("tok_offset", C.c_void_p), ("embed_table", C.c_void_p), ("vocab", C.c_int64),
+        ("attention_mask", C.c_void_p), ("mask_mode", C.c_int32), ("label_mode", C.c_int32),
+        ("labels_in", C.c_void_p), ("label_len", C.c_int32), ("reserved", C.c_int32),
+        ("labels_out", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+class ConnectorError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (message from avc_last_error())."""
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree shared library; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ConnectorError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "The connector has no PyTorch/CPU fallback.")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.avc_abi_version.restype = C.c_int
+    lib.avc_last_error.restype = C.c_char_p
+    lib.avc_colsum_workspace_bytes.restype = C.c_size_t
+    lib.avc_colsum_workspace_bytes.argtypes = [C.c_int32]
+    if lib.avc_abi_version() != AVC_ABI_VERSION:
+        raise ConnectorError(f"ABI version mismatch: library {lib.avc_abi_version()} != binding {AVC_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise ConnectorError(f"avconnector_b200 error {rc}: {load().avc_last_error().decode()}")
+
+
+def require_device(index: int = 0) -> None:
+    """Replaces the reference's `"cuda" if torch.cuda.is_available() else "cpu"` (clip_whisper_model.py:91)."""
+    check(load().avc_device_check(index))
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def mat(t: torch.Tensor) -> AvcMat:
+    """2-D [rows, cols] or 3-D [batches, rows, cols] tensor (cols contiguous) -> avc_mat."""
+    if t.dim() == 2:
+        if t.stride(1) != 1:
+            raise ValueError("matrix columns must be contiguous")
+        return AvcMat(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 1, t.shape[0] * t.stride(0))
+    if t.dim() == 3:
+        if t.stride(2) != 1:
+            raise ValueError("matrix columns must be contiguous")
+        return AvcMat(t.data_ptr(), t.shape[1], t.shape[2], t.stride(1), t.shape[0], t.stride(0))
+    raise ValueError("expected a 2-D or 3-D tensor")
+
+
+def feat(t: Optional[torch.Tensor], stack: int, valid: Optional[torch.Tensor] = None) -> Optional[AvcFeat]:
+    """[batch, frames, dim] bf16 features (any batch/frame stride, dim contiguous) -> avc_feat."""
+    if t is None:
+        return None
+    if t.dim() != 3 or t.stride(2) != 1 or t.dtype != torch.bfloat16:
+        raise ValueError("features must be bf16 [batch, frames, dim] with contiguous dim")
+    if valid is not None and (valid.dtype != torch.int32 or not valid.is_contiguous()):
+        raise ValueError("valid_frames must be a contiguous int32 tensor")
+    return AvcFeat(t.data_ptr(), t.stride(0), t.stride(1), t.shape[1], t.shape[2], stack, 0, _ptr(valid))
+
+
+def _mat_array(ms: Sequence[AvcMat]):
+    return (AvcMat * len(ms))(*ms)
+
+
+# ------------------------------------------------------------------------------------------ kernels
+def gather_fwd(audio, video, ka: int, kv: int, batch: int, tokens_per_sample: int, a_out: torch.Tensor,
+               row_flags: Optional[torch.Tensor] = None, tok_offset: Optional[torch.Tensor] = None,
+               audio_valid=None, video_valid=None) -> None:
+    fa, fv = feat(audio, ka, audio_valid), feat(video, kv, video_valid)
+    check(load().avc_gather_fwd(
+        C.byref(fa) if fa is not None else None, C.byref(fv) if fv is not None else None, C.c_int32(batch),
+        C.c_void_p(_ptr(tok_offset)), C.c_int32(tokens_per_sample), C.c_int64(a_out.shape[0]),
+        C.c_void_p(a_out.data_ptr()), C.c_int64(a_out.stride(0)), C.c_void_p(_ptr(row_flags)), stream_ptr()))
+
+
+def proj_fwd(a_segs: Sequence[torch.Tensor], w_segs: Sequence[torch.Tensor], y: torch.Tensor,
+             bias0: Optional[torch.Tensor] = None, bias1: Optional[torch.Tensor] = None,
+             row_flags: Optional[torch.Tensor] = None, flag_rows0: int = 1 << 30, flag_rows1: int = 1 << 30,
+             act: int = 0) -> None:
+    check(load().avc_proj_fwd(
+        C.c_int32(len(a_segs)), _mat_array([mat(t) for t in a_segs]), _mat_array([mat(t) for t in w_segs]),
+        C.byref(mat(y)), C.c_int32(1 if y.dtype == torch.float32 else 0), C.c_void_p(_ptr(bias0)),
+        C.c_void_p(_ptr(bias1)), C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
+        C.c_int32(act), stream_ptr()))
+
+
+def proj_bwd_dw(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
+                alpha: Sequence[float], dy_row_base: int = 0) -> None:
+    al = (C.c_float * len(x_segs))(*alpha)
+    check(load().avc_proj_bwd_dw(
+        C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
+        _mat_array([mat(t) for t in dw_segs]), al, stream_ptr()))
+
+
+def colsum_workspace(cols: int, device) -> torch.Tensor:
+    n = load().avc_colsum_workspace_bytes(cols)
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
+def colsum(dy: torch.Tensor, out0: Optional[torch.Tensor], out1: Optional[torch.Tensor], workspace: torch.Tensor,
+           row_flags: Optional[torch.Tensor] = None, flag_rows0: int = 1 << 30, flag_rows1: int = 1 << 30,
+           alpha0: float = 1.0, alpha1: float = 1.0) -> None:
+    check(load().avc_colsum(
+        C.byref(mat(dy)), C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
+        C.c_float(alpha0), C.c_float(alpha1), C.c_void_p(_ptr(out0)), C.c_void_p(_ptr(out1)),
+        C.c_void_p(workspace.data_ptr()), stream_ptr()))
+
+
+def pack_weight(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> None:
+    """dst_bf16[r, c] = bf16(alpha * src_f32[r, c]); dst may be a column slice of a wider matrix."""
+    check(load().avc_pack_weight(
+        C.c_void_p(src.data_ptr()), C.c_int64(src.stride(0)), C.c_void_p(dst.data_ptr()), C.c_int64(dst.stride(0)),
+        C.c_int64(src.shape[0]), C.c_int64(src.shape[1]), C.c_float(alpha), stream_ptr()))
+
+
+def make_splice(input_ids: torch.Tensor, placeholder_id: int, pad_id: int, hidden: int, tokens_per_sample: int = 0,
+                tok_offset=None, embed_table=None, attention_mask=None, mask_mode: int = 0, label_mode: int = 0,
+                labels_in=None, labels_out=None, status=None) -> AvcSplice:
+    b, s = input_ids.shape
+    return AvcSplice(
+        input_ids.data_ptr(), placeholder_id, pad_id, b, s, hidden, tokens_per_sample, _ptr(tok_offset),
+        _ptr(embed_table), 0 if embed_table is None else embed_table.shape[0], _ptr(attention_mask), mask_mode,
+        label_mode, _ptr(labels_in), 0 if labels_in is None else labels_in.shape[1], 0, _ptr(labels_out),
+        _ptr(status))
+
+
+def splice_fwd(s: AvcSplice, y: Optional[torch.Tensor], inputs_embeds: torch.Tensor) -> None:
+    check(load().avc_splice_fwd(C.byref(s), C.c_void_p(_ptr(y)), C.c_void_p(inputs_embeds.data_ptr()), stream_ptr()))
+
+
+def splice_bwd(s: AvcSplice, d_inputs_embeds: torch.Tensor, dy: torch.Tensor) -> None:
+    check(load().avc_splice_bwd(C.byref(s), C.c_void_p(d_inputs_embeds.data_ptr()), C.c_void_p(dy.data_ptr()),
+                                stream_ptr()))

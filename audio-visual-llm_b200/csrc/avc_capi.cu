@@ -1,0 +1,370 @@
+// C ABI of the B200-native clip_whisper connector (include/avconnector_b200.h).
+// Validates arguments, builds TMA tensor maps, and enqueues the sm_100a kernels on the caller's
+// stream.  Nothing here allocates device memory, synchronises, or falls back to the CPU.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include "../../include/avconnector_b200.h"
+#include "avc_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(AVC_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int cc_major = 0;
+};
+
+// current device's properties, cached per device id
+int device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(AVC_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache[dev].device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    e = cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(sm count)");
+    e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(cc major)");
+    cache[dev] = d;
+  }
+  *out = cache[dev];
+  if (out->cc_major != 10)
+    return fail(AVC_ERR_UNSUPPORTED,
+                "device %d has compute capability %d.x; this library only runs on sm_100 (B200) "
+                "and has no CPU or other-GPU fallback",
+                dev, out->cc_major);
+  return AVC_OK;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+// 3-D tensor map over [batches][rows][cols] (cols contiguous), 128-byte swizzle.
+int make_map3d(CUtensorMap* map, const void* ptr, bool fp32, int64_t cols, int64_t rows,
+               int64_t batches, int64_t row_stride_elems, int64_t batch_stride_elems, int box_cols,
+               int box_rows, const char* what) {
+  auto enc = encode_fn();
+  if (enc == nullptr) return fail(AVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int64_t es = fp32 ? 4 : 2;
+  if (ptr == nullptr) return fail(AVC_ERR_INVALID, "%s: null pointer", what);
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(AVC_ERR_INVALID, "%s: base not 16-byte aligned", what);
+  if (cols <= 0 || rows <= 0 || batches <= 0) return fail(AVC_ERR_INVALID, "%s: empty extent", what);
+  if ((row_stride_elems * es) % 16 != 0 || row_stride_elems < cols)
+    return fail(AVC_ERR_INVALID, "%s: row stride %lld must be >= cols and a multiple of 16 bytes", what,
+                static_cast<long long>(row_stride_elems));
+  if (batches == 1) batch_stride_elems = rows * row_stride_elems;
+  if ((batch_stride_elems * es) % 16 != 0)
+    return fail(AVC_ERR_INVALID, "%s: batch stride must be a multiple of 16 bytes", what);
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(batches)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems * es),
+                           static_cast<cuuint64_t>(batch_stride_elems * es)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(AVC_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, static_cast<int>(r));
+  return AVC_OK;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+extern "C" {
+
+int avc_abi_version(void) { return AVC_ABI_VERSION; }
+
+const char* avc_last_error(void) { return g_err; }
+
+int avc_device_check(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (device < 0 || device >= count)
+    return fail(AVC_ERR_UNSUPPORTED, "no CUDA device %d (found %d); there is no CPU fallback", device, count);
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10)
+    return fail(AVC_ERR_UNSUPPORTED, "device %d is compute capability %d.x, need 10.x (sm_100a)", device, major);
+  return AVC_OK;
+}
+
+int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t batch, const int32_t* tok_offset,
+                   int32_t tokens_per_sample, int64_t total_rows, void* a_out, int64_t a_row_stride,
+                   uint8_t* row_flags, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (batch <= 0) return fail(AVC_ERR_INVALID, "gather: batch must be positive");
+  if (a_out == nullptr) return fail(AVC_ERR_INVALID, "gather: null output");
+  if (tok_offset == nullptr && tokens_per_sample <= 0)
+    return fail(AVC_ERR_INVALID, "gather: tokens_per_sample must be positive when tok_offset is NULL");
+  if (tok_offset == nullptr && total_rows != static_cast<int64_t>(batch) * tokens_per_sample)
+    return fail(AVC_ERR_INVALID, "gather: total_rows != batch * tokens_per_sample");
+  avc::GatherArgs g;
+  memset(&g, 0, sizeof(g));
+  const avc_feat* f[2] = {audio, video};
+  int64_t k_total = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (f[i] == nullptr || f[i]->ptr == nullptr) continue;
+    if (f[i]->dim <= 0 || f[i]->dim % 8 != 0)
+      return fail(AVC_ERR_INVALID, "gather: feature dim %d must be a positive multiple of 8", f[i]->dim);
+    if (f[i]->stack < 1 || f[i]->frames < 0) return fail(AVC_ERR_INVALID, "gather: bad stack / frames");
+    if (f[i]->frame_stride < f[i]->dim) return fail(AVC_ERR_INVALID, "gather: frame stride < dim");
+    g.src[i] = static_cast<const uint8_t*>(f[i]->ptr);
+    g.batch_stride[i] = f[i]->batch_stride * 2;
+    g.frame_stride[i] = f[i]->frame_stride * 2;
+    g.frame_bytes[i] = f[i]->dim * 2;
+    g.frames[i] = f[i]->frames;
+    g.k[i] = f[i]->stack;
+    g.len[i] = f[i]->valid_frames;
+    k_total += static_cast<int64_t>(f[i]->stack) * f[i]->dim;
+  }
+  if (k_total == 0) return fail(AVC_ERR_INVALID, "gather: both modalities absent");
+  if (a_row_stride < k_total)
+    return fail(AVC_ERR_INVALID, "gather: output row stride %lld < stacked width %lld",
+                static_cast<long long>(a_row_stride), static_cast<long long>(k_total));
+  g.tok_offset = tok_offset;
+  g.tokens_per_sample = tokens_per_sample;
+  g.batch = batch;
+  g.total_rows = total_rows;
+  g.dst = static_cast<uint8_t*>(a_out);
+  g.dst_row_bytes = a_row_stride * 2;
+  g.row_flags = row_flags;
+  cudaError_t e = avc::launch_gather(g, di.num_sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "gather launch");
+  return AVC_OK;
+}
+
+int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat* y, int32_t y_is_fp32,
+                 const float* bias0, const float* bias1, const uint8_t* row_flags, int32_t flag_rows0,
+                 int32_t flag_rows1, int32_t act, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (nseg < 1 || nseg > 2) return fail(AVC_ERR_INVALID, "proj_fwd: nseg must be 1 or 2");
+  if (a == nullptr || w == nullptr || y == nullptr) return fail(AVC_ERR_INVALID, "proj_fwd: null matrix");
+  if (act != 0 && act != 1) return fail(AVC_ERR_INVALID, "proj_fwd: act must be 0 or 1");
+  const int64_t N = y->cols;
+  if (N <= 0 || N % 8 != 0) return fail(AVC_ERR_INVALID, "proj_fwd: N must be a positive multiple of 8");
+  if (y->rows <= 0 || y->batches <= 0) return fail(AVC_ERR_INVALID, "proj_fwd: empty output");
+  avc::GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    if (a[s].cols != w[s].cols)
+      return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: A has K=%lld but W has K=%lld", s,
+                  static_cast<long long>(a[s].cols), static_cast<long long>(w[s].cols));
+    if (w[s].rows != N) return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: W rows != N", s);
+    if (a[s].batches != y->batches) return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: batch mismatch", s);
+    if (a[s].cols % 8 != 0) return fail(AVC_ERR_INVALID, "proj_fwd: K must be a multiple of 8");
+    if (int rc = make_map3d(&g.ma[s], a[s].ptr, false, a[s].cols, a[s].rows, a[s].batches, a[s].row_stride,
+                            a[s].batch_stride, avc::GEMM_BK, avc::GEMM_BM, "proj_fwd A"))
+      return rc;
+    if (int rc = make_map3d(&g.mb[s], w[s].ptr, false, w[s].cols, w[s].rows, 1, w[s].row_stride, 0,
+                            avc::GEMM_BK, avc::GEMM_BN, "proj_fwd W"))
+      return rc;
+    g.seg_kblocks[s] = static_cast<int>(ceil_div(a[s].cols, avc::GEMM_BK));
+  }
+  if (int rc = make_map3d(&g.md[0], y->ptr, y_is_fp32 != 0, N, y->rows, y->batches, y->row_stride,
+                          y->batch_stride, y_is_fp32 ? 32 : 64, 32, "proj_fwd Y"))
+    return rc;
+  g.m_tiles_per_batch = static_cast<int>(ceil_div(y->rows, avc::GEMM_BM));
+  g.num_m_blocks = static_cast<int>(y->batches) * g.m_tiles_per_batch;
+  g.num_n_blocks = static_cast<int>(ceil_div(N, avc::GEMM_BN));
+  g.d_rows = static_cast<int>(y->rows);
+  g.d_cols[0] = static_cast<int>(N);
+  g.d_cols[1] = static_cast<int>(N);
+  g.bias0 = bias0;
+  g.bias1 = bias1;
+  g.row_flags = row_flags;
+  g.flag_rows0 = flag_rows0;
+  g.flag_rows1 = flag_rows1;
+  g.alpha[0] = g.alpha[1] = 1.f;
+  g.act = act;
+  if ((bias0 && (reinterpret_cast<uintptr_t>(bias0) & 15)) || (bias1 && (reinterpret_cast<uintptr_t>(bias1) & 15)))
+    return fail(AVC_ERR_INVALID, "proj_fwd: bias pointers must be 16-byte aligned");
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, y_is_fp32 != 0, di.num_sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "proj_fwd launch");
+  return AVC_OK;
+}
+
+int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
+                    const float* alpha, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (nseg < 1 || nseg > 2) return fail(AVC_ERR_INVALID, "proj_bwd_dw: nseg must be 1 or 2");
+  if (dy == nullptr || x == nullptr || dw == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw: null matrix");
+  const int64_t H = dy->cols;
+  if (H <= 0 || H % 8 != 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: H must be a positive multiple of 8");
+  if (dy_row_base < 0 || dy_row_base >= dy->rows) return fail(AVC_ERR_INVALID, "proj_bwd_dw: dy_row_base out of range");
+  avc::GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.nseg = nseg;
+  if (int rc = make_map3d(&g.ma[0], dy->ptr, false, H, dy->rows, dy->batches, dy->row_stride, dy->batch_stride,
+                          64, avc::GEMM_BK, "proj_bwd_dw dY"))
+    return rc;
+  int64_t red_rows = 0;
+  int n_blocks[2] = {0, 0};
+  for (int s = 0; s < nseg; ++s) {
+    if (x[s].batches != dy->batches) return fail(AVC_ERR_INVALID, "proj_bwd_dw: segment %d: batch mismatch", s);
+    if (x[s].cols % 8 != 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: K must be a multiple of 8");
+    if (dw[s].rows != H || dw[s].cols != x[s].cols)
+      return fail(AVC_ERR_INVALID, "proj_bwd_dw: segment %d: dW must be [H, K]", s);
+    if (int rc = make_map3d(&g.mb[s], x[s].ptr, false, x[s].cols, x[s].rows, x[s].batches, x[s].row_stride,
+                            x[s].batch_stride, 64, avc::GEMM_BK, "proj_bwd_dw X"))
+      return rc;
+    if (int rc = make_map3d(&g.md[s], dw[s].ptr, true, dw[s].cols, dw[s].rows, 1, dw[s].row_stride, 0, 32, 32,
+                            "proj_bwd_dw dW"))
+      return rc;
+    red_rows = x[s].rows > red_rows ? x[s].rows : red_rows;
+    n_blocks[s] = static_cast<int>(ceil_div(x[s].cols, avc::GEMM_BN));
+    g.d_cols[s] = static_cast<int>(x[s].cols);
+    g.alpha[s] = alpha != nullptr ? alpha[s] : 1.f;
+  }
+  g.num_m_blocks = static_cast<int>(ceil_div(H, avc::GEMM_BM));
+  g.num_n_blocks = n_blocks[0] + n_blocks[1];
+  g.n_blocks_seg0 = n_blocks[0];
+  g.red_batches = static_cast<int>(dy->batches);
+  g.red_kblocks_per_batch = static_cast<int>(ceil_div(red_rows, avc::GEMM_BK));
+  g.a_row_base = dy_row_base;
+  g.d_rows = static_cast<int>(H);
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, di.num_sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "proj_bwd_dw launch");
+  return AVC_OK;
+}
+
+size_t avc_colsum_workspace_bytes(int32_t cols) { return avc::colsum_workspace_bytes(cols); }
+
+int avc_colsum(const avc_mat* dy, const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, float alpha0,
+               float alpha1, float* out0, float* out1, void* workspace, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (dy == nullptr || dy->ptr == nullptr) return fail(AVC_ERR_INVALID, "colsum: null dY");
+  if (workspace == nullptr) return fail(AVC_ERR_INVALID, "colsum: null workspace");
+  avc::ColsumArgs c;
+  memset(&c, 0, sizeof(c));
+  c.dy = static_cast<const uint8_t*>(dy->ptr);
+  c.row_stride = dy->row_stride * 2;
+  c.batch_stride = dy->batch_stride * 2;
+  c.batch = static_cast<int>(dy->batches);
+  c.rows = static_cast<int>(dy->rows);
+  c.cols = static_cast<int>(dy->cols);
+  c.row_flags = row_flags;
+  c.flag_rows0 = flag_rows0;
+  c.flag_rows1 = flag_rows1;
+  c.alpha0 = alpha0;
+  c.alpha1 = alpha1;
+  c.out0 = out0;
+  c.out1 = out1;
+  c.workspace = static_cast<float*>(workspace);
+  cudaError_t e = avc::launch_colsum(c, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "colsum launch");
+  return AVC_OK;
+}
+
+int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows, int64_t cols,
+                    float alpha, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (src == nullptr || dst_bf16 == nullptr) return fail(AVC_ERR_INVALID, "pack_weight: null pointer");
+  cudaError_t e = avc::launch_pack_weight(src, src_ld, dst_bf16, dst_ld, rows, cols, alpha,
+                                          static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "pack_weight launch");
+  return AVC_OK;
+}
+
+static int fill_splice(const avc_splice* s, avc::SpliceArgs* k) {
+  if (s == nullptr || s->input_ids == nullptr) return fail(AVC_ERR_INVALID, "splice: null input_ids");
+  if (s->hidden <= 0 || s->hidden % 8 != 0) return fail(AVC_ERR_INVALID, "splice: hidden must be a positive multiple of 8");
+  if (s->batch <= 0 || s->seq <= 0) return fail(AVC_ERR_INVALID, "splice: empty batch / seq");
+  if (s->tok_offset == nullptr && s->tokens_per_sample < 0)
+    return fail(AVC_ERR_INVALID, "splice: negative tokens_per_sample");
+  memset(k, 0, sizeof(*k));
+  k->input_ids = s->input_ids;
+  k->placeholder_id = s->placeholder_id;
+  k->pad_id = s->pad_id;
+  k->batch = s->batch;
+  k->seq = s->seq;
+  k->row_bytes = s->hidden * 2;
+  k->tok_offset = s->tok_offset;
+  k->tokens_per_sample = s->tokens_per_sample;
+  k->embed_table = static_cast<const uint8_t*>(s->embed_table);
+  k->vocab = s->vocab;
+  k->attention_mask = s->attention_mask;
+  k->mask_mode = s->mask_mode;
+  k->labels_in = s->labels_in;
+  k->label_len = s->label_len;
+  k->labels_out = s->labels_out;
+  k->label_mode = s->label_mode;
+  k->status = s->status;
+  return AVC_OK;
+}
+
+int avc_splice_fwd(const avc_splice* s, const void* y, void* inputs_embeds, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  avc::SpliceArgs k;
+  if (int rc = fill_splice(s, &k)) return rc;
+  if (inputs_embeds == nullptr) return fail(AVC_ERR_INVALID, "splice_fwd: null inputs_embeds");
+  k.y = static_cast<const uint8_t*>(y);
+  k.inputs_embeds = static_cast<uint8_t*>(inputs_embeds);
+  cudaError_t e = avc::launch_splice_fwd(k, di.num_sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "splice_fwd launch");
+  return AVC_OK;
+}
+
+int avc_splice_bwd(const avc_splice* s, const void* d_inputs_embeds, void* dy, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  avc::SpliceArgs k;
+  if (int rc = fill_splice(s, &k)) return rc;
+  if (d_inputs_embeds == nullptr || dy == nullptr) return fail(AVC_ERR_INVALID, "splice_bwd: null pointer");
+  k.inputs_embeds = const_cast<uint8_t*>(static_cast<const uint8_t*>(d_inputs_embeds));
+  k.dy = static_cast<uint8_t*>(dy);
+  k.attention_mask = nullptr;
+  k.labels_out = nullptr;
+  cudaError_t e = avc::launch_splice_bwd(k, di.num_sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "splice_bwd launch");
+  return AVC_OK;
+}
+
+}  // extern "C"

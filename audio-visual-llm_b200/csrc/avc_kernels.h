@@ -1,0 +1,121 @@
+// Internal launch interface between the C-ABI layer (avc_capi.cu) and the sm_100a kernels.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace avc {
+
+// ------------------------------------------------------------------ projector GEMM (tcgen05)
+constexpr int GEMM_BM = 128;  // UMMA M (TMEM lanes)
+constexpr int GEMM_BN = 256;  // UMMA N (TMEM columns per accumulator stage)
+constexpr int GEMM_BK = 64;   // contraction elements per smem stage (= one 128-byte swizzle row)
+
+enum GemmMode : int {
+  GEMM_TN = 0,  // D[m,n] = sum_k A[m,k] * B[n,k]      (both operands K-major)   -> forward, dX-free
+  GEMM_NT = 1,  // D[m,n] = sum_r A[r,m] * B[r,n]      (both operands MN-major)  -> dW = dY^T * X
+};
+
+struct GemmArgs {
+  CUtensorMap ma[2];  // TN: A operand per K segment.        NT: ma[0] = dY  ([batch][rows][m])
+  CUtensorMap mb[2];  // TN: B operand (weights) per K seg.  NT: X per output segment ([batch][rows][n])
+  CUtensorMap md[2];  // TN: md[0] = output.                 NT: output per segment
+  int num_m_blocks;
+  int num_n_blocks;
+  // TN
+  int m_tiles_per_batch;  // an M tile never straddles two batch entries
+  int nseg;               // K segments
+  int seg_kblocks[2];
+  // NT
+  int red_batches;            // batches reduced over
+  int red_kblocks_per_batch;  // ceil(rows_per_batch / GEMM_BK)
+  int a_row_base;             // first dY row of the token run inside each batch entry
+  int n_blocks_seg0;          // N tiles that belong to output segment 0
+  // output extents (stores that start outside are skipped; partial boxes are clipped by TMA)
+  int d_rows;     // TN: rows per batch entry.  NT: rows of D
+  int d_cols[2];  // TN: d_cols[0] = N.         NT: columns of D per segment
+  // epilogue
+  const float* bias0;        // [N] fp32, added where flag bit0 is set (nullptr: none)
+  const float* bias1;        // [N] fp32, added where flag bit1 is set (nullptr: none)
+  const uint8_t* row_flags;  // packed-row mode: flags[batch * d_rows + row]; nullptr: analytic
+  int flag_rows0;            // analytic: bit0 = row < flag_rows0
+  int flag_rows1;            // analytic: bit1 = row < flag_rows1
+  float alpha[2];            // NT: output scale per segment
+  int act;                   // 0 = identity, 1 = GELU (erf form)
+};
+
+size_t gemm_smem_bytes();
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int max_ctas,
+                        cudaStream_t stream);
+
+// ------------------------------------------------------------------ gather (align + stack + concat)
+struct GatherArgs {
+  const uint8_t* src[2];      // audio, video feature bases (bytes); nullptr: modality absent
+  int64_t batch_stride[2];    // bytes
+  int64_t frame_stride[2];    // bytes
+  int frame_bytes[2];         // D * sizeof(bf16)
+  int frames[2];              // T per modality (upper bound on valid frames)
+  int k[2];                   // frames stacked per token
+  const int32_t* len[2];      // optional per-sample valid frame counts (device), nullptr: frames[i]
+  const int32_t* tok_offset;  // [B+1] packed row offsets (device), nullptr: uniform tokens_per_sample
+  int tokens_per_sample;      // uniform mode
+  int batch;
+  int64_t total_rows;         // M
+  uint8_t* dst;               // A [M, K] bytes
+  int64_t dst_row_bytes;      // K * 2
+  uint8_t* row_flags;         // [M] (bit0 audio token present, bit1 video token present), may be null
+};
+cudaError_t launch_gather(const GatherArgs& args, int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------ splice (scatter + masks)
+struct SpliceArgs {
+  const int64_t* input_ids;   // [B, S]
+  int64_t placeholder_id;
+  int64_t pad_id;
+  int batch, seq;             // B, S
+  int row_bytes;              // H * 2
+  const int32_t* tok_offset;  // [B+1] or nullptr (uniform)
+  int tokens_per_sample;
+  // forward: Y rows + embedding table -> inputs_embeds
+  const uint8_t* y;           // [M, H] projected rows (fwd) ; nullptr in bwd
+  const uint8_t* embed_table; // [V, H] bf16, may be null (text rows zero-filled)
+  int64_t vocab;
+  uint8_t* inputs_embeds;     // [B, S, H] (fwd: out; bwd: grad in)
+  uint8_t* dy;                // bwd: [M, H] out
+  // masks
+  int64_t* attention_mask;    // [B, S] out (fwd) may be null
+  int mask_mode;              // 0 = all ones (reference), 1 = valid tokens only
+  const int64_t* labels_in;   // [B, L] may be null
+  int label_len;              // L
+  int64_t* labels_out;        // [B, S] may be null
+  int label_mode;             // 0 = reference (pad->-100, truncate / right-pad -100), 1 = causal-LM
+  int32_t* status;            // device int: set to nonzero on malformed input (placeholder count)
+};
+cudaError_t launch_splice_fwd(const SpliceArgs& args, int num_sms, cudaStream_t stream);
+cudaError_t launch_splice_bwd(const SpliceArgs& args, int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------ small elementwise / reductions
+// dst_bf16[r, c] = bf16(alpha * src_f32[r, c]),  src ld = src_ld, dst ld = dst_ld (elements)
+cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int64_t dst_ld,
+                               int64_t rows, int64_t cols, float alpha, cudaStream_t stream);
+// dst_bf16 = bf16(src_f32) / dst_f32 = float(src_bf16), contiguous n elements
+cudaError_t launch_cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
+
+// Column sums of dY over flagged rows, deterministic two-pass:
+//   out0[c] = alpha0 * sum_{r : flag bit0} dY[r, c],  out1[c] = alpha1 * sum_{r : flag bit1} dY[r, c]
+struct ColsumArgs {
+  const uint8_t* dy;         // [batch][rows][H] bf16
+  int64_t row_stride;        // bytes
+  int64_t batch_stride;      // bytes
+  int batch, rows, cols;     // rows per batch entry
+  const uint8_t* row_flags;  // [batch*rows] or nullptr (analytic)
+  int flag_rows0, flag_rows1;
+  float alpha0, alpha1;
+  float* out0;               // [cols] may be null
+  float* out1;               // [cols] may be null
+  float* workspace;          // colsum_workspace_bytes()
+};
+size_t colsum_workspace_bytes(int cols);
+cudaError_t launch_colsum(const ColsumArgs& args, cudaStream_t stream);
+
+}  // namespace avc

@@ -1,0 +1,131 @@
+// Small HBM-bound helpers around the projector GEMMs:
+//   pack_weight : W_bf16 = bf16(alpha * W_fp32)   (folds fusion_scale of clip_whisper_model.py:434 into the weights)
+//   colsum      : db = alpha * sum over flagged rows of dY   (autograd of the nn.Linear bias,
+//                 modality_connector.py:32, with the pad-after-projection row mask of
+//                 clip_whisper_model.py:340-345)
+#include "avc_kernels.h"
+#include "avc_ptx.cuh"
+
+namespace avc {
+
+namespace {
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ src, int64_t src_ld,
+                                                          uint8_t* __restrict__ dst, int64_t dst_ld,
+                                                          int64_t rows, int64_t cols, float alpha) {
+  // one thread = 8 consecutive columns of one row (two float4 loads, one 16-byte store)
+  const int64_t groups_per_row = cols >> 3;
+  const int64_t total = rows * groups_per_row;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / groups_per_row;
+    const int64_t c = (g - r * groups_per_row) << 3;
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(src + r * src_ld + c));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(src + r * src_ld + c + 4));
+    int4 o;
+    o.x = static_cast<int>(pack_bf16x2(x0.x * alpha, x0.y * alpha));
+    o.y = static_cast<int>(pack_bf16x2(x0.z * alpha, x0.w * alpha));
+    o.z = static_cast<int>(pack_bf16x2(x1.x * alpha, x1.y * alpha));
+    o.w = static_cast<int>(pack_bf16x2(x1.z * alpha, x1.w * alpha));
+    *reinterpret_cast<int4*>(dst + (r * dst_ld + c) * 2) = o;
+  }
+}
+
+constexpr int CS_THREADS = 256;
+constexpr int CS_MAX_CHUNKS = 296;
+
+__device__ __forceinline__ void acc_bf16x8(float (&s)[8], const int4& v) {
+  const uint32_t w[4] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y),
+                         static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[2 * i + 0] += __uint_as_float(w[i] << 16);
+    s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// partial[chunk][which][col]
+__global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(const __grid_constant__ ColsumArgs a,
+                                                                    int rows_per_chunk) {
+  const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * rows_per_chunk;
+  int64_t g1 = g0 + rows_per_chunk;
+  g1 = g1 < total_rows ? g1 : total_rows;
+  const int col = (blockIdx.y * CS_THREADS + threadIdx.x) * 8;
+  if (col >= a.cols) return;
+  float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t g = g0; g < g1; ++g) {
+    const int b = static_cast<int>(g / a.rows);
+    const int r = static_cast<int>(g - static_cast<int64_t>(b) * a.rows);
+    bool f0, f1;
+    if (a.row_flags != nullptr) {
+      const uint8_t fl = __ldg(a.row_flags + g);
+      f0 = fl & 1; f1 = fl & 2;
+    } else {
+      f0 = r < a.flag_rows0; f1 = r < a.flag_rows1;
+    }
+    if (!(f0 || f1)) continue;
+    const int4 v = ld_nc_v4(a.dy + b * a.batch_stride + r * a.row_stride + static_cast<int64_t>(col) * 2);
+    if (f0) acc_bf16x8(s0, v);
+    if (f1) acc_bf16x8(s1, v);
+  }
+  float* p0 = a.workspace + (static_cast<int64_t>(blockIdx.x) * 2 + 0) * a.cols + col;
+  float* p1 = a.workspace + (static_cast<int64_t>(blockIdx.x) * 2 + 1) * a.cols + col;
+  *reinterpret_cast<float4*>(p0) = make_float4(s0[0], s0[1], s0[2], s0[3]);
+  *reinterpret_cast<float4*>(p0 + 4) = make_float4(s0[4], s0[5], s0[6], s0[7]);
+  *reinterpret_cast<float4*>(p1) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  *reinterpret_cast<float4*>(p1 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+}
+
+__global__ void __launch_bounds__(CS_THREADS) colsum_final_kernel(const __grid_constant__ ColsumArgs a,
+                                                                  int nchunks) {
+  const int col = blockIdx.x * CS_THREADS + threadIdx.x;
+  if (col >= a.cols) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = 0; c < nchunks; ++c) {  // fixed order: deterministic
+    s0 += a.workspace[(static_cast<int64_t>(c) * 2 + 0) * a.cols + col];
+    s1 += a.workspace[(static_cast<int64_t>(c) * 2 + 1) * a.cols + col];
+  }
+  if (a.out0 != nullptr) a.out0[col] = a.alpha0 * s0;
+  if (a.out1 != nullptr) a.out1[col] = a.alpha1 * s1;
+}
+
+}  // namespace
+
+cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int64_t dst_ld,
+                               int64_t rows, int64_t cols, float alpha, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  if (cols % 8 != 0 || src_ld % 4 != 0 || dst_ld % 8 != 0 ||
+      (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0)
+    return cudaErrorMisalignedAddress;
+  const int64_t total = rows * (cols >> 3);
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_weight_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
+      src, src_ld, static_cast<uint8_t*>(dst), dst_ld, rows, cols, alpha);
+  return cudaGetLastError();
+}
+
+size_t colsum_workspace_bytes(int cols) {
+  return static_cast<size_t>(CS_MAX_CHUNKS) * 2 * static_cast<size_t>(cols) * sizeof(float);
+}
+
+cudaError_t launch_colsum(const ColsumArgs& a, cudaStream_t stream) {
+  if (a.cols <= 0) return cudaSuccess;
+  if (a.cols % 8 != 0 || a.row_stride % 16 != 0 || a.batch_stride % 16 != 0 ||
+      (reinterpret_cast<uintptr_t>(a.dy) & 15) != 0 || a.workspace == nullptr)
+    return cudaErrorMisalignedAddress;
+  const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows;
+  int nchunks = static_cast<int>(total_rows < CS_MAX_CHUNKS ? (total_rows > 0 ? total_rows : 1) : CS_MAX_CHUNKS);
+  const int rows_per_chunk = static_cast<int>((total_rows + nchunks - 1) / (nchunks > 0 ? nchunks : 1));
+  if (rows_per_chunk > 0) nchunks = static_cast<int>((total_rows + rows_per_chunk - 1) / rows_per_chunk);
+  if (nchunks < 1) nchunks = 1;
+  dim3 grid(nchunks, (a.cols / 8 + CS_THREADS - 1) / CS_THREADS);
+  colsum_partial_kernel<<<grid, CS_THREADS, 0, stream>>>(a, rows_per_chunk > 0 ? rows_per_chunk : 1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  colsum_final_kernel<<<(a.cols + CS_THREADS - 1) / CS_THREADS, CS_THREADS, 0, stream>>>(a, nchunks);
+  return cudaGetLastError();
+}
+
+}  // namespace avc

@@ -1,0 +1,193 @@
+// Gather: temporal align + stride-k frame stacking + feature concat, one pass, HBM-bound.
+//
+//   A[m, :] = [ audio[b, k_a*j .. k_a*j+k_a-1, :]  ;  video[b, k_v*j .. k_v*j+k_v-1, :] ]   m = (b, j)
+//
+// Frames at or beyond the sample's valid length are zero.  With k_a = k_v = 1 this is the reference's
+// index-by-index alignment + zero pad of the shorter stream (clip_whisper_model.py:424-431); a video
+// frame stride of (1+Np)*Dv also folds in the CLS-row select of clip_whisper_model.py:1141-1142.
+//
+// Data never touches registers: each warp runs a ring of smem stages; one elected lane issues
+// cp.async.bulk (TMA, global->smem, mbarrier complete_tx) loads two items ahead and
+// cp.async.bulk (smem->global, bulk_group) stores behind.  Padding comes from a zeroed smem block.
+#include "avc_kernels.h"
+#include "avc_ptx.cuh"
+
+namespace avc {
+
+namespace {
+
+constexpr int G_WARPS = 4;
+constexpr int G_STAGES = 4;
+constexpr int G_LOOKAHEAD = 2;  // loads in flight per warp; stage reuse distance = G_STAGES - 2 stores
+
+struct Item {
+  const uint8_t* src;
+  uint8_t* dst;
+  int nvalid;   // frames to copy
+  int nzero;    // frames to zero-fill
+  int mod;
+};
+
+__device__ __forceinline__ void locate_row(const GatherArgs& a, int64_t m, int& b, int& j) {
+  if (a.tok_offset == nullptr) {
+    b = static_cast<int>(m / a.tokens_per_sample);
+    j = static_cast<int>(m - static_cast<int64_t>(b) * a.tokens_per_sample);
+    return;
+  }
+  int lo = 0, hi = a.batch;  // find b with tok_offset[b] <= m < tok_offset[b+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a.tok_offset + mid) <= m) lo = mid; else hi = mid;
+  }
+  b = lo;
+  j = static_cast<int>(m - __ldg(a.tok_offset + lo));
+}
+
+__device__ __forceinline__ int valid_len(const GatherArgs& a, int mod, int b) {
+  int len = a.frames[mod];
+  if (a.len[mod] != nullptr) {
+    const int l = __ldg(a.len[mod] + b);
+    len = l < len ? l : len;
+    len = len < 0 ? 0 : len;
+  }
+  return len;
+}
+
+__global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_constant__ GatherArgs a, int nmods,
+                                                               int mod0, int stage_bytes,
+                                                               int zero_bytes) {
+  extern __shared__ __align__(128) uint8_t g_smem[];
+  // layout: [zero block][warp rings][barriers]
+  const uint32_t s_zero = smem_u32(g_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_ring = s_zero + zero_bytes + warp * (G_STAGES * stage_bytes);
+  const uint32_t s_bar = s_zero + zero_bytes + G_WARPS * G_STAGES * stage_bytes +
+                         warp * (G_STAGES * 8);
+
+  for (int i = threadIdx.x * 16; i < zero_bytes; i += blockDim.x * 16)
+    st_shared_v4(s_zero + i, 0u, 0u, 0u, 0u);
+  if (lane == 0) {
+    for (int s = 0; s < G_STAGES; ++s) mbar_init(s_bar + 8 * s, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  if (lane == 0) {
+    const int64_t total_items = a.total_rows * nmods;
+    const int64_t gwarps = static_cast<int64_t>(gridDim.x) * G_WARPS;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * G_WARPS + warp;
+    const int64_t my_items = gw < total_items ? (total_items - gw + gwarps - 1) / gwarps : 0;
+    const int64_t seg1_off = (a.src[0] != nullptr) ? static_cast<int64_t>(a.k[0]) * a.frame_bytes[0] : 0;
+
+    auto make_item = [&](int64_t n) {
+      Item it;
+      const int64_t id = gw + n * gwarps;
+      const int64_t m = id / nmods;
+      it.mod = (nmods == 2) ? static_cast<int>(id - m * 2) : mod0;
+      int b, j;
+      locate_row(a, m, b, j);
+      const int mod = it.mod;
+      const int len = valid_len(a, mod, b);
+      const int64_t f0 = static_cast<int64_t>(j) * a.k[mod];
+      int64_t nv = len - f0;
+      nv = nv < 0 ? 0 : (nv > a.k[mod] ? a.k[mod] : nv);
+      it.nvalid = static_cast<int>(nv);
+      it.nzero = a.k[mod] - it.nvalid;
+      it.src = a.src[mod] + b * a.batch_stride[mod] + f0 * a.frame_stride[mod];
+      it.dst = a.dst + m * a.dst_row_bytes + (mod == 1 ? seg1_off : 0);
+      if (a.row_flags != nullptr && (nmods == 1 || mod == 0)) {
+        uint8_t fl = 0;
+        if (a.src[0] != nullptr) {
+          const int la = (mod == 0) ? len : valid_len(a, 0, b);
+          if (static_cast<int64_t>(j) * a.k[0] < la) fl |= 1;
+        }
+        if (a.src[1] != nullptr) {
+          const int lv = (mod == 1) ? len : valid_len(a, 1, b);
+          if (static_cast<int64_t>(j) * a.k[1] < lv) fl |= 2;
+        }
+        a.row_flags[m] = fl;
+      }
+      return it;
+    };
+    auto issue_load = [&](const Item& it, int64_t n) {
+      if (it.nvalid == 0) return;
+      const int s = static_cast<int>(n % G_STAGES);
+      const uint32_t bar = s_bar + 8 * s;
+      const uint32_t buf = s_ring + s * stage_bytes;
+      const int fb = a.frame_bytes[it.mod];
+      mbar_arrive_expect_tx(bar, static_cast<uint32_t>(it.nvalid * fb));
+      if (a.frame_stride[it.mod] == fb) {
+        bulk_g2s(buf, it.src, static_cast<uint32_t>(it.nvalid * fb), bar);
+      } else {
+        for (int f = 0; f < it.nvalid; ++f)
+          bulk_g2s(buf + f * fb, it.src + f * a.frame_stride[it.mod], fb, bar);
+      }
+    };
+
+    // loads run G_LOOKAHEAD items ahead of stores
+    for (int64_t n = 0; n < G_LOOKAHEAD && n < my_items; ++n) issue_load(make_item(n), n);
+    uint32_t phase_bits = 0;  // bit s = parity of the next load phase to wait for on stage s
+    for (int64_t n = 0; n < my_items; ++n) {
+      const int64_t na = n + G_LOOKAHEAD;
+      if (na < my_items) {
+        // stage (na % G_STAGES) was last read by the store of item na - G_STAGES = n - 2
+        bulk_wait_read<G_STAGES - G_LOOKAHEAD - 1>();
+        issue_load(make_item(na), na);
+      }
+      const Item it = make_item(n);
+      const int s = static_cast<int>(n % G_STAGES);
+      const int fb = a.frame_bytes[it.mod];
+      if (it.nvalid > 0) {
+        mbar_wait(s_bar + 8 * s, (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+        bulk_s2g(it.dst, s_ring + s * stage_bytes, static_cast<uint32_t>(it.nvalid * fb));
+      }
+      for (int f = 0; f < it.nzero; ++f)
+        bulk_s2g(it.dst + static_cast<int64_t>(it.nvalid + f) * fb, s_zero, fb);
+      bulk_commit();
+    }
+    bulk_wait_all<0>();
+  }
+  __syncwarp();
+}
+
+}  // namespace
+
+cudaError_t launch_gather(const GatherArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.total_rows <= 0) return cudaSuccess;
+  const int nmods = (a.src[0] != nullptr ? 1 : 0) + (a.src[1] != nullptr ? 1 : 0);
+  if (nmods == 0) return cudaErrorInvalidValue;
+  const int mod0 = a.src[0] != nullptr ? 0 : 1;
+  int stage_bytes = 0, zero_bytes = 16;
+  for (int i = 0; i < 2; ++i) {
+    if (a.src[i] == nullptr) continue;
+    if (a.frame_bytes[i] % 16 != 0 || a.frame_stride[i] % 16 != 0 || a.batch_stride[i] % 16 != 0 ||
+        (reinterpret_cast<uintptr_t>(a.src[i]) & 15) != 0)
+      return cudaErrorMisalignedAddress;
+    const int seg = a.k[i] * a.frame_bytes[i];
+    stage_bytes = seg > stage_bytes ? seg : stage_bytes;
+    zero_bytes = a.frame_bytes[i] > zero_bytes ? a.frame_bytes[i] : zero_bytes;
+  }
+  if ((reinterpret_cast<uintptr_t>(a.dst) & 15) != 0 || a.dst_row_bytes % 16 != 0)
+    return cudaErrorMisalignedAddress;
+  stage_bytes = (stage_bytes + 127) & ~127;
+  zero_bytes = (zero_bytes + 127) & ~127;
+  const size_t smem = static_cast<size_t>(zero_bytes) + G_WARPS * G_STAGES * stage_bytes +
+                      G_WARPS * G_STAGES * 8;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int64_t total_items = a.total_rows * nmods;
+  int64_t grid = static_cast<int64_t>(num_sms) * ctas_per_sm;
+  const int64_t need = (total_items + G_WARPS - 1) / G_WARPS;
+  if (grid > need) grid = need;
+  gather_kernel<<<static_cast<int>(grid), G_WARPS * 32, smem, stream>>>(a, nmods, mod0, stage_bytes,
+                                                                         zero_bytes);
+  return cudaGetLastError();
+}
+
+}  // namespace avc

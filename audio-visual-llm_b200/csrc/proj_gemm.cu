@@ -1,0 +1,329 @@
+// Projector GEMMs for the clip_whisper connector on sm_100a.
+//
+//   forward  (GEMM_TN):  Y[b, r, n] = act( sum_seg  A_seg[b, r, :] . W_seg[n, :]  + flag0*bias0[n] + flag1*bias1[n] )
+//   backward (GEMM_NT):  dW_seg[h, k] = alpha_seg * sum_{b, r} dY[b, r, h] * X_seg[b, r, k]
+//
+// This replaces the two nn.Linear calls + pad + weighted sum of the reference
+// (modality_connector.py:43-44, clip_whisper_model.py:424-434) and their autograd dW.
+//
+// Structure: persistent CTAs (one per SM), 6 warps:
+//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages of 48 KB)
+//   warp 1      tcgen05.mma issuer (one thread), owns the TMEM allocation (512 columns = 2 accumulators)
+//   warps 2..5  epilogue: tcgen05.ld (TMEM -> registers) -> bias/GELU/scale -> swizzled smem -> TMA store
+// The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "avc_kernels.h"
+#include "avc_ptx.cuh"
+
+namespace avc {
+
+namespace {
+
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;                       // 32 rows x 128 B per warp per buffer
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;      // 32 KB
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_USED = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+constexpr int SMEM_ALLOC = SMEM_USED + 1024;  // slack for manual 1024-B alignment
+constexpr int kThreads = 32 * (2 + EPI_WARPS);
+constexpr int MN_ATOM_BYTES = BK * 128;  // one 64-wide MN-major atom column: BK rows x 128 B
+
+static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of dynamic shared memory");
+static_assert(kAccStages * BN <= kTmemCols, "accumulators exceed TMEM");
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int MODE, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_epi = smem_base + kStages * STAGE_BYTES;
+  const uint32_t s_bar = s_epi + EPI_BYTES;
+  auto full_bar = [&](uint32_t s) { return s_bar + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return s_bar + 8u * (kStages + s); };
+  auto tfull_bar = [&](uint32_t a) { return s_bar + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](uint32_t a) { return s_bar + 8u * (2 * kStages + kAccStages + a); };
+  const uint32_t s_tmem_slot = s_bar + 8u * (2 * kStages + 2 * kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&args.ma[0]);
+    tma_prefetch_desc(&args.mb[0]);
+    tma_prefetch_desc(&args.md[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < kAccStages; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), EPI_WARPS);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(s_tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_slot));
+
+  const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+  const int total_kb = (MODE == GEMM_TN)
+                           ? (args.seg_kblocks[0] + (args.nseg > 1 ? args.seg_kblocks[1] : 0))
+                           : (args.red_batches * args.red_kblocks_per_batch);
+
+  if (warp == 0) {
+    // ======================================================================= TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / args.num_n_blocks;
+        const int n_blk = tile % args.num_n_blocks;
+        if (MODE == GEMM_TN) {
+          const int b = m_blk / args.m_tiles_per_batch;
+          const int r0 = (m_blk % args.m_tiles_per_batch) * BM;
+          const int n0 = n_blk * BN;
+          for (int seg = 0; seg < args.nseg; ++seg) {
+            for (int kb = 0; kb < args.seg_kblocks[seg]; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+              const uint32_t sa = smem_base + stage * STAGE_BYTES;
+              tma_load_3d(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b);
+              tma_load_3d(sa + A_STAGE_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        } else {
+          const int m0 = m_blk * BM;
+          const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
+          const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * BN;
+          for (int bb = 0; bb < args.red_batches; ++bb) {
+            for (int kb = 0; kb < args.red_kblocks_per_batch; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+              const uint32_t sa = smem_base + stage * STAGE_BYTES;
+              const int row = kb * BK;
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_3d(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64,
+                            args.a_row_base + row, bb);
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_3d(sa + A_STAGE_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage),
+                            nl0 + i * 64, row, bb);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc =
+          make_idesc_bf16(BM, BN, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < total_kb; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            uint64_t da, db;
+            if (MODE == GEMM_TN) {
+              // K-major: 8-row x 128-B swizzle atoms stacked along M/N (SBO = 1024 B); stepping
+              // UMMA_K = 16 elements inside the 128-B row is +32 B on the start address.
+              da = make_smem_desc_sw128(sa + kk * (UMMA_K * 2), 0, 1024);
+              db = make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 0, 1024);
+            } else {
+              // MN-major: each contraction row is one 128-B swizzle row of 64 M/N elements;
+              // 8 rows per atom (SBO = 1024 B), next 64 M/N elements at LBO = BK*128 B;
+              // UMMA_K = 16 contraction rows = +2048 B.
+              da = make_smem_desc_sw128(sa + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
+              db = make_smem_desc_sw128(sb + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
+            }
+            umma_f16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================================================= epilogue warps
+    const int q = warp & 3;    // TMEM lane quarter this warp may access
+    const int ew = warp - 2;   // staging buffer owner index
+    constexpr int COLS = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
+    constexpr int NCHUNK = BN / COLS;
+    uint32_t acc = 0, acc_phase = 0, buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / args.num_n_blocks;
+      const int n_blk = tile % args.num_n_blocks;
+      int out_row0, out_batch, out_col0, seg = 0;
+      if (MODE == GEMM_TN) {
+        out_batch = m_blk / args.m_tiles_per_batch;
+        out_row0 = (m_blk % args.m_tiles_per_batch) * BM + q * 32;
+        out_col0 = n_blk * BN;
+      } else {
+        out_batch = 0;
+        out_row0 = m_blk * BM + q * 32;
+        seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
+        out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * BN;
+      }
+      const int my_row = out_row0 + lane;
+      float f0 = 0.f, f1 = 0.f;
+      if (MODE == GEMM_TN) {
+        if (args.row_flags != nullptr) {
+          if (my_row < args.d_rows) {
+            const uint8_t fl = args.row_flags[static_cast<int64_t>(out_batch) * args.d_rows + my_row];
+            f0 = (fl & 1) ? 1.f : 0.f;
+            f1 = (fl & 2) ? 1.f : 0.f;
+          }
+        } else {
+          f0 = my_row < args.flag_rows0 ? 1.f : 0.f;
+          f1 = my_row < args.flag_rows1 ? 1.f : 0.f;
+        }
+        if (args.bias0 == nullptr) f0 = 0.f;
+        if (args.bias1 == nullptr) f1 = 0.f;
+      }
+      const float alpha = args.alpha[seg];
+      const int ncols = args.d_cols[seg];
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col = out_col0 + c * COLS;
+        // the store issued from this staging buffer two chunks ago must have finished reading it
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const uint32_t sbuf = s_epi + (ew * 2 + buf) * EPI_BUF_BYTES;
+        const uint32_t srow = sbuf + lane * 128;
+        // COLS accumulator columns of this thread's row -> registers
+        uint32_t v[COLS];
+        {
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          tmem_ld_32x32(t_row + c * COLS, v0);
+          if (!OUT_F32) {
+            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[COLS - 32]);
+            tmem_ld_32x32(t_row + c * COLS + 32, v1);
+          }
+          tmem_ld_wait();
+        }
+        float x[COLS];
+#pragma unroll
+        for (int g = 0; g < COLS / 4; ++g) {
+          float* xg = &x[4 * g];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xg[e] = __uint_as_float(v[4 * g + e]);
+          if (MODE == GEMM_TN) {
+            const int n = col + 4 * g;
+            if (n < ncols) {
+              if (f0 != 0.f) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias0 + n));
+                xg[0] += b.x; xg[1] += b.y; xg[2] += b.z; xg[3] += b.w;
+              }
+              if (f1 != 0.f) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias1 + n));
+                xg[0] += b.x; xg[1] += b.y; xg[2] += b.z; xg[3] += b.w;
+              }
+            }
+            if (args.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xg[e] = gelu_erf(xg[e]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xg[e] *= alpha;
+          }
+        }
+        // one 128-byte staging row per thread, 16-byte chunks XOR-swizzled (matches SWIZZLE_128B)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = srow + ((j ^ (lane & 7)) << 4);
+          if (OUT_F32) {
+            st_shared_v4(dst, __float_as_uint(x[4 * j + 0]), __float_as_uint(x[4 * j + 1]),
+                         __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+          } else {
+            const int o = (8 * j) % COLS;  // (COLS == 64 here)
+            st_shared_v4(dst, pack_bf16x2(x[o + 0], x[o + 1]), pack_bf16x2(x[o + 2], x[o + 3]),
+                         pack_bf16x2(x[o + 4], x[o + 5]), pack_bf16x2(x[o + 6], x[o + 7]));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (out_row0 < args.d_rows && col < ncols)
+            tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
+          bulk_commit();
+        }
+        buf ^= 1u;
+      }
+      // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+size_t gemm_smem_bytes() { return SMEM_ALLOC; }
+
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int max_ctas,
+                        cudaStream_t stream) {
+  const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+  if (num_tiles <= 0) return cudaSuccess;
+  const int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
+  auto run = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kThreads, SMEM_ALLOC, stream>>>(args);
+    return cudaGetLastError();
+  };
+  if (mode == GEMM_TN) {
+    return out_fp32 ? run(gemm_kernel<GEMM_TN, true>) : run(gemm_kernel<GEMM_TN, false>);
+  }
+  return out_fp32 ? run(gemm_kernel<GEMM_NT, true>) : run(gemm_kernel<GEMM_NT, false>);
+}
+
+}  // namespace avc

@@ -1,0 +1,145 @@
+/* avconnector_b200.h -- C ABI of the B200-native clip_whisper multimodal connector.
+ *
+ * The reference (rishabhjain16/audio-visual-llm) has no FFI: its connector is plain PyTorch
+ * (src/clip_whisper/models/modality_connector.py, clip_whisper_model.py).  This header is the
+ * boundary a maintainer would bind instead of those eager ops (INTEGRATION.md shows the ctypes stub).
+ * Each entry point names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; nothing is allocated or freed
+ *   - feature / weight / embedding elements are bf16; masks, ids and labels are int64 (reference dtype)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
+ *   - return 0 on success, non-zero on error; avc_last_error() gives the message (thread-local)
+ *   - there is no CPU fallback: a device that is not sm_100 is an error
+ */
+#ifndef AVCONNECTOR_B200_H_
+#define AVCONNECTOR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AVC_API __attribute__((visibility("default")))
+#else
+#define AVC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVC_ABI_VERSION 1
+
+enum avc_status {
+  AVC_OK = 0,
+  AVC_ERR_INVALID = 1,      /* bad argument (shape, alignment, null) */
+  AVC_ERR_CUDA = 2,         /* CUDA runtime / driver error */
+  AVC_ERR_UNSUPPORTED = 3   /* not an sm_100 device, or a size outside kernel limits */
+};
+
+AVC_API int avc_abi_version(void);
+AVC_API const char* avc_last_error(void);
+/* AVC_OK iff `device` is a compute-capability 10.x GPU.  Replaces the reference's
+ * `"cuda" if torch.cuda.is_available() else "cpu"` fallback (clip_whisper_model.py:91). */
+AVC_API int avc_device_check(int device);
+
+/* One modality's tower output: bf16 [batch, frames, dim]. */
+typedef struct avc_feat {
+  const void* ptr;             /* NULL: modality absent */
+  int64_t batch_stride;        /* elements between samples */
+  int64_t frame_stride;        /* elements between frames: dim if dense; (1+Np)*dim selects the CLS row
+                                  of a CLIP last_hidden_state (clip_whisper_model.py:1141-1142) */
+  int32_t frames;              /* T */
+  int32_t dim;                 /* D, multiple of 8 */
+  int32_t stack;               /* k >= 1 frames stacked per token (k = 1: reference behaviour) */
+  int32_t reserved;
+  const int32_t* valid_frames; /* [batch] per-sample valid frame count, or NULL (= frames) */
+} avc_feat;
+
+/* A strided bf16 / fp32 matrix batch: [batches][rows][cols], cols contiguous. */
+typedef struct avc_mat {
+  void* ptr;
+  int64_t rows;          /* rows per batch entry */
+  int64_t cols;
+  int64_t row_stride;    /* elements */
+  int64_t batches;       /* 1 for a plain matrix */
+  int64_t batch_stride;  /* elements */
+} avc_mat;
+
+/* ---- gather: temporal align + stride-k stack + concat (HBM-bound, TMA bulk copies) ---------------
+ * A[m, :] = [audio[b, ka*j .. ka*j+ka-1, :] ; video[b, kv*j .. kv*j+kv-1, :]], m = tok_offset[b] + j,
+ * frames past the valid length are zero.  row_flags[m] bit0/bit1 = row has an audio / video token.
+ * Replaces _pad_or_truncate + index alignment (clip_whisper_model.py:320-374, 424-431), moved in
+ * front of the projection (exact: padding rows are zero and their bias is masked via row_flags). */
+AVC_API int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t batch,
+                   const int32_t* tok_offset /* [batch+1] or NULL */, int32_t tokens_per_sample,
+                   int64_t total_rows, void* a_out, int64_t a_row_stride, uint8_t* row_flags,
+                   void* stream);
+
+/* ---- projector forward (tensor-core bound, tcgen05 + TMEM + TMA) -------------------------------
+ * Y[b, r, :] = act( sum_s A_s[b, r, :] . W_s^T  + flag0(b,r) * bias0 + flag1(b,r) * bias1 )
+ * flags come from row_flags (packed rows) or, if NULL, flag_i = (r < flag_rows_i).
+ * Replaces SimpleModalityConnector.forward x2 + weighted sum (modality_connector.py:43-44,
+ * clip_whisper_model.py:434) through W = [fs*Wa | (1-fs)*Wv], bias0 = fs*ba, bias1 = (1-fs)*bv. */
+AVC_API int avc_proj_fwd(int32_t nseg, const avc_mat* a /* [nseg] bf16 */, const avc_mat* w /* [nseg] bf16 [N, K_s] */,
+                 const avc_mat* y, int32_t y_is_fp32, const float* bias0, const float* bias1,
+                 const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1,
+                 int32_t act /* 0 none, 1 GELU(erf) */, void* stream);
+
+/* ---- projector backward: weight gradient ------------------------------------------------------
+ * dW_s[h, k] = alpha_s * sum_{b, r < x.rows} dY[b, dy_row_base + r, h] * X_s[b, r, k]   (fp32 out)
+ * Replaces autograd of nn.Linear (dW = dY^T X); dX is not produced (towers are frozen,
+ * clip_whisper_model.py:1096,1136). */
+AVC_API int avc_proj_bwd_dw(const avc_mat* dy /* bf16 [b][rows][H] */, int32_t dy_row_base, int32_t nseg,
+                    const avc_mat* x /* [nseg] bf16 */, const avc_mat* dw /* [nseg] fp32 [H, K_s] */,
+                    const float* alpha /* [nseg] */, void* stream);
+
+/* ---- bias gradient: deterministic two-pass column sum over flagged rows ------------------------- */
+AVC_API size_t avc_colsum_workspace_bytes(int32_t cols);
+AVC_API int avc_colsum(const avc_mat* dy /* bf16 */, const uint8_t* row_flags, int32_t flag_rows0,
+               int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1,
+               void* workspace, void* stream);
+
+/* ---- weight pack: W_bf16 = bf16(alpha * W_fp32) (folds fusion_scale into the projector) -------- */
+AVC_API int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows,
+                    int64_t cols, float alpha, void* stream);
+
+/* ---- splice: scatter projected rows + text embeddings into inputs_embeds, emit masks ------------
+ * inputs_embeds[b, p] = Y[tok_offset[b] + rank(p)]  where input_ids[b, p] == placeholder_id
+ *                     = embed_table[input_ids[b, p]] elsewhere (zeros if no table / id out of range)
+ * attention_mask (int64): mask_mode 0 -> all ones (clip_whisper_model.py:460); 1 -> valid tokens only
+ * labels_out (int64):  label_mode 0 -> reference eval rule: pad -> -100, truncate / right-pad -100
+ *                      (clip_whisper_model.py:569-570, 586-598); 1 -> also -100 on placeholders
+ * *status (device int32) gets bit0 if a sample's placeholder count != its token count.
+ * Replaces _embed_prompt + torch.cat + torch.ones (clip_whisper_model.py:448-451, 460, 464-487). */
+typedef struct avc_splice {
+  const int64_t* input_ids;   /* [batch, seq] */
+  int64_t placeholder_id;
+  int64_t pad_id;
+  int32_t batch;
+  int32_t seq;
+  int32_t hidden;             /* H, multiple of 8 */
+  int32_t tokens_per_sample;  /* used when tok_offset is NULL */
+  const int32_t* tok_offset;  /* [batch+1] or NULL */
+  const void* embed_table;    /* bf16 [vocab, H] or NULL */
+  int64_t vocab;
+  int64_t* attention_mask;    /* [batch, seq] or NULL */
+  int32_t mask_mode;
+  int32_t label_mode;
+  const int64_t* labels_in;   /* [batch, label_len] or NULL */
+  int32_t label_len;
+  int32_t reserved;
+  int64_t* labels_out;        /* [batch, seq] or NULL */
+  int32_t* status;            /* device int32 or NULL */
+} avc_splice;
+
+AVC_API int avc_splice_fwd(const avc_splice* s, const void* y /* bf16 [M, H] */, void* inputs_embeds,
+                   void* stream);
+/* dY[tok_offset[b] + rank(p)] = d_inputs_embeds[b, p] at placeholder positions (autograd of the cat). */
+AVC_API int avc_splice_bwd(const avc_splice* s, const void* d_inputs_embeds, void* dy /* bf16 [M, H] */,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVCONNECTOR_B200_H_ */

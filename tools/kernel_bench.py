@@ -1,0 +1,94 @@
+"""Per-kernel timing at the BASELINE cfg2 shapes (CUDA events, L2 flushed between iterations).
+Usage (GPU box): python tools/kernel_bench.py [--iters N]   -> one JSON line per kernel."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import __graft_entry__ as entry  # noqa: E402
+
+entry.build()
+import audio_visual_llm_b200 as pkg  # noqa: E402
+
+L = pkg._lib
+
+
+def timed(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=32)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    L.require_device(0)
+    peaks = json.loads((Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").read_text()) \
+        if (Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    B, Ta, Tv, Da, Dv, H, ka, kv, P = args.batch, 1500, 750, 1024, 1024, 4096, 4, 2, 16
+    N = Ta // ka
+    M, K, S = B * N, ka * Da + kv * Dv, P + N
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    audio = torch.randn(B, Ta, Da, device=dev).to(torch.bfloat16)
+    video = torch.randn(B, Tv, Dv, device=dev).to(torch.bfloat16)
+    A = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+    flags = torch.empty(M, dtype=torch.uint8, device=dev)
+    W = (torch.randn(H, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(H, device=dev)
+    Y = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+    dW = torch.empty(H, K, dtype=torch.float32, device=dev)
+    ids = torch.cat([torch.randint(1, 1000, (B, P), device=dev), torch.full((B, N), 32000, device=dev)], 1)
+    table = torch.randn(32001, H, device=dev).to(torch.bfloat16)
+    emb = torch.empty(B, S, H, dtype=torch.bfloat16, device=dev)
+    mask = torch.empty(B, S, dtype=torch.int64, device=dev)
+    labels = torch.empty(B, S, dtype=torch.int64, device=dev)
+    sp = L.make_splice(ids, 32000, 0, H, tokens_per_sample=N, embed_table=table, attention_mask=mask, labels_out=labels)
+    d_emb = torch.randn(B, S, H, device=dev).to(torch.bfloat16)
+    dY = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+    ws = L.colsum_workspace(H, dev)
+    db = torch.empty(H, dtype=torch.float32, device=dev)
+
+    def report(name, fn, nbytes=None, flops=None):
+        med, best = timed(fn, args.iters, flush)
+        rec = {"kernel": name, "ms_median": round(med, 4), "ms_min": round(best, 4)}
+        if nbytes:
+            rec["GBps"] = round(nbytes / med / 1e6, 1)
+            rec["frac_hbm_measured"] = round(nbytes / med / 1e6 / peaks["hbm_gbs"], 3)
+        if flops:
+            rec["TFLOPs"] = round(flops / med / 1e9, 1)
+            rec["frac_bf16_measured_burst"] = round(flops / med / 1e9 / peaks["bf16_tflops"], 3)
+        print(json.dumps(rec), flush=True)
+
+    report("gather", lambda: L.gather_fwd(audio, video, ka, kv, B, N, A, flags), nbytes=2 * M * K * 2)
+    report("proj_fwd", lambda: L.proj_fwd([A], [W], Y, bias0=bias), flops=2 * M * K * H)
+    report("proj_fwd_2seg", lambda: L.proj_fwd([A[:, :ka * Da], A[:, ka * Da:]], [W[:, :ka * Da], W[:, ka * Da:]], Y,
+                                               bias0=bias, bias1=bias, row_flags=flags), flops=2 * M * K * H)
+    report("proj_fwd_gelu", lambda: L.proj_fwd([A], [W], Y, bias0=bias, act=1), flops=2 * M * K * H)
+    report("splice_fwd", lambda: L.splice_fwd(sp, Y, emb), nbytes=2 * B * S * H * 2 + 16 * B * S)
+    report("splice_bwd", lambda: L.splice_bwd(sp, d_emb, dY), nbytes=2 * M * H * 2)
+    report("proj_bwd_dw", lambda: L.proj_bwd_dw(dY, [A], [dW], [1.0]), flops=2 * M * K * H)
+    report("colsum", lambda: L.colsum(dY, db, None, ws), nbytes=M * H * 2)
+    report("torch_matmul_fwd", lambda: torch.matmul(A, W.t(), out=Y), flops=2 * M * K * H)
+    dWb = torch.empty(H, K, dtype=torch.bfloat16, device=dev)
+    report("torch_matmul_dw", lambda: torch.matmul(dY.t(), A, out=dWb), flops=2 * M * K * H)
+
+
+if __name__ == "__main__":
+    main()
