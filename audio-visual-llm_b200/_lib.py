@@ -177,11 +177,14 @@ def make_splice(input_ids: torch.Tensor, placeholder_id: int, pad_id: int, hidde
                 tok_offset=None, embed_table=None, attention_mask=None, mask_mode: int = 0, label_mode: int = 0,
                 labels_in=None, labels_out=None, status=None) -> AvcSplice:
     b, s = input_ids.shape
-    return AvcSplice(
+    sp = AvcSplice(
         input_ids.data_ptr(), placeholder_id, pad_id, b, s, hidden, tokens_per_sample, _ptr(tok_offset),
         _ptr(embed_table), 0 if embed_table is None else embed_table.shape[0], _ptr(attention_mask), mask_mode,
         label_mode, _ptr(labels_in), 0 if labels_in is None else labels_in.shape[1], 0, _ptr(labels_out),
         _ptr(status))
+    # the struct only holds raw pointers: keep the tensors alive as long as the descriptor is
+    sp._keep = (input_ids, tok_offset, embed_table, attention_mask, labels_in, labels_out, status)
+    return sp
 
 
 def splice_fwd(s: AvcSplice, y: Optional[torch.Tensor], inputs_embeds: torch.Tensor) -> None:
