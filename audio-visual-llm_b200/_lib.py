@@ -18,7 +18,7 @@ AVC_ABI_VERSION = 1
 EXPORTS = (
     "avc_abi_version", "avc_last_error", "avc_device_check", "avc_gather_fwd", "avc_proj_fwd",
     "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",
-    "avc_splice_bwd",
+    "avc_splice_bwd", "avc_row_resample",
 )
 
 
@@ -43,7 +43,7 @@ class AvcSplice(C.Structure):
         ("batch", C.c_int32), ("seq", C.c_int32), ("hidden", C.c_int32), ("tokens_per_sample", C.c_int32),
         ("tok_offset", C.c_void_p), ("embed_table", C.c_void_p), ("vocab", C.c_int64),
         ("attention_mask", C.c_void_p), ("mask_mode", C.c_int32), ("label_mode", C.c_int32),
-        ("labels_in", C.c_void_p), ("label_len", C.c_int32), ("reserved", C.c_int32),
+        ("labels_in", C.c_void_p), ("label_len", C.c_int32), ("elem_size", C.c_int32),
         ("labels_out", C.c_void_p), ("status", C.c_void_p),
     ]
 
@@ -136,12 +136,12 @@ def gather_fwd(audio, video, ka: int, kv: int, batch: int, tokens_per_sample: in
 def proj_fwd(a_segs: Sequence[torch.Tensor], w_segs: Sequence[torch.Tensor], y: torch.Tensor,
              bias0: Optional[torch.Tensor] = None, bias1: Optional[torch.Tensor] = None,
              row_flags: Optional[torch.Tensor] = None, flag_rows0: int = 1 << 30, flag_rows1: int = 1 << 30,
-             act: int = 0) -> None:
+             act: int = 0, bias_scale0: float = 1.0, bias_scale1: float = 1.0) -> None:
     check(load().avc_proj_fwd(
         C.c_int32(len(a_segs)), _mat_array([mat(t) for t in a_segs]), _mat_array([mat(t) for t in w_segs]),
         C.byref(mat(y)), C.c_int32(1 if y.dtype == torch.float32 else 0), C.c_void_p(_ptr(bias0)),
-        C.c_void_p(_ptr(bias1)), C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
-        C.c_int32(act), stream_ptr()))
+        C.c_void_p(_ptr(bias1)), C.c_float(bias_scale0), C.c_float(bias_scale1), C.c_void_p(_ptr(row_flags)),
+        C.c_int32(flag_rows0), C.c_int32(flag_rows1), C.c_int32(act), stream_ptr()))
 
 
 def proj_bwd_dw(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
@@ -175,12 +175,12 @@ def pack_weight(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> Non
 
 def make_splice(input_ids: torch.Tensor, placeholder_id: int, pad_id: int, hidden: int, tokens_per_sample: int = 0,
                 tok_offset=None, embed_table=None, attention_mask=None, mask_mode: int = 0, label_mode: int = 0,
-                labels_in=None, labels_out=None, status=None) -> AvcSplice:
+                labels_in=None, labels_out=None, status=None, elem_size: int = 2) -> AvcSplice:
     b, s = input_ids.shape
     sp = AvcSplice(
         input_ids.data_ptr(), placeholder_id, pad_id, b, s, hidden, tokens_per_sample, _ptr(tok_offset),
         _ptr(embed_table), 0 if embed_table is None else embed_table.shape[0], _ptr(attention_mask), mask_mode,
-        label_mode, _ptr(labels_in), 0 if labels_in is None else labels_in.shape[1], 0, _ptr(labels_out),
+        label_mode, _ptr(labels_in), 0 if labels_in is None else labels_in.shape[1], elem_size, _ptr(labels_out),
         _ptr(status))
     # the struct only holds raw pointers: keep the tensors alive as long as the descriptor is
     sp._keep = (input_ids, tok_offset, embed_table, attention_mask, labels_in, labels_out, status)
@@ -194,3 +194,15 @@ def splice_fwd(s: AvcSplice, y: Optional[torch.Tensor], inputs_embeds: torch.Ten
 def splice_bwd(s: AvcSplice, d_inputs_embeds: torch.Tensor, dy: torch.Tensor) -> None:
     check(load().avc_splice_bwd(C.byref(s), C.c_void_p(d_inputs_embeds.data_ptr()), C.c_void_p(dy.data_ptr()),
                                 stream_ptr()))
+
+
+def row_resample(x: torch.Tensor, out: torch.Tensor, row_ptr: torch.Tensor, col_idx: torch.Tensor,
+                 weight: torch.Tensor) -> None:
+    """out[b, i, :] = sum_t weight[t] * x[b, col_idx[t], :] over CSR row i; x [B, S, H], out [B, L, H] contiguous."""
+    if not (x.is_contiguous() and out.is_contiguous()) or x.dtype != out.dtype:
+        raise ValueError("row_resample needs contiguous tensors of one dtype")
+    es = {torch.bfloat16: 2, torch.float32: 4}[x.dtype]
+    check(load().avc_row_resample(
+        C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int32(es), C.c_int32(x.shape[0]),
+        C.c_int32(x.shape[1]), C.c_int32(out.shape[1]), C.c_int32(x.shape[2]), C.c_void_p(row_ptr.data_ptr()),
+        C.c_void_p(col_idx.data_ptr()), C.c_void_p(weight.data_ptr()), stream_ptr()))

@@ -1,0 +1,328 @@
+"""Drop-in `ClipWhisperModel` for the connector path of the reference's
+src/clip_whisper/models/clip_whisper_model.py: same `encode / encode_audio / encode_video / forward / generate`
+interface, constructor keywords and attributes, with the connector (align -> stack -> fuse -> project -> splice
++ masks) running as sm_100a CUDA.  Whisper, CLIP and the LLM stay untouched PyTorch modules and are called
+exactly where the reference calls them (clip_whisper_model.py:1098-1103, 1138, 601-613, 1337-1340).
+
+New keyword arguments default to the reference's behaviour:
+  fusion="sum" | "concat"      stride=1 (frames stacked per token)      align="index" | "rate"
+  audio_stride / video_stride  (override stride/align)                   mask_mode / label_mode (0 = reference)
+`align="rate"` pairs 2 Whisper frames (50 Hz) with 1 CLIP frame (25 fps): k_a = stride, k_v = stride / 2.
+
+There is no CPU fallback (the reference's `"cuda" if torch.cuda.is_available() else "cpu"` default,
+clip_whisper_model.py:91, is removed): the device must be an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .connector_ops import MAX_PROMPT_LEN, FusePlan, fused_connector
+from .modality_connector import create_modality_connector
+from .seq_adapt import adapt_mask, adaptive_projection
+
+
+class ClipWhisperModel(nn.Module):
+    def __init__(
+        self,
+        llm_path: str = "meta-llama/Llama-2-7b-chat-hf",
+        whisper_model: str = "openai/whisper-medium",
+        clip_model: str = "openai/clip-vit-base-patch32",
+        device: str = "cuda",
+        use_fp16: bool = False,
+        use_4bit: bool = False,
+        use_lora: bool = True,
+        lora_r: int = 16,
+        lora_alpha: int = 32,
+        lora_dropout: float = 0.05,
+        freeze_encoders: bool = True,
+        freeze_llm: bool = False,
+        modality: str = "both",
+        max_seq_len: int = 256,
+        fusion_scale: float = 0.5,
+        connector_type: str = "simple",
+        _provided_tokenizer=None,
+        _provided_llm=None,
+        _provided_whisper=None,
+        _provided_clip=None,
+        # ---- new keys (defaults = reference behaviour)
+        fusion: str = "sum",
+        stride: int = 1,
+        align: str = "index",
+        audio_stride: Optional[int] = None,
+        video_stride: Optional[int] = None,
+        mask_mode: int = 0,
+        label_mode: int = 0,
+        audio_dim: Optional[int] = None,
+        video_dim: Optional[int] = None,
+    ):
+        super().__init__()
+        if not str(device).startswith("cuda"):
+            raise L.ConnectorError(f"device={device!r}: the B200 connector path has no CPU fallback")
+        idx = torch.device(device).index
+        L.require_device(0 if idx is None else idx)
+        if not freeze_encoders:
+            raise NotImplementedError("freeze_encoders=False needs input gradients (dX), which this path does not "
+                                      "produce; the reference default is True (configs/clip_whisper.yaml:28)")
+        if align not in ("index", "rate"):
+            raise ValueError("align must be 'index' or 'rate'")
+        self.device = device
+        self.use_fp16 = use_fp16
+        self.freeze_encoders = freeze_encoders
+        self.freeze_llm = freeze_llm
+        self.modality = modality
+        self.max_seq_len = max_seq_len
+        self.fusion_scale = fusion_scale
+        self.connector_type = connector_type
+        self.fusion = fusion
+        ka = audio_stride if audio_stride is not None else stride
+        if video_stride is not None:
+            kv = video_stride
+        elif align == "rate":
+            if stride % 2:
+                raise ValueError("align='rate' needs an even stride (2 audio frames per video frame)")
+            kv = stride // 2
+        else:
+            kv = stride
+        self.audio_stride, self.video_stride = ka, kv
+        self.mask_mode, self.label_mode = mask_mode, label_mode
+        self.dtype = torch.bfloat16 if use_fp16 else torch.float32  # reference: fp16 if use_fp16 (:164)
+
+        self.tokenizer = _provided_tokenizer
+        self.llm = _provided_llm
+        self.whisper = _provided_whisper
+        self.clip = _provided_clip
+        if self.llm is None or self.tokenizer is None:
+            self.tokenizer, self.llm = self._load_llm(llm_path)
+        if self.whisper is None and modality in ("audio", "both"):
+            self.whisper = self._load_tower("WhisperModel", whisper_model)
+        if self.clip is None and modality in ("video", "both"):
+            self.clip = self._load_tower("CLIPVisionModel", clip_model)
+        for tower in (self.whisper, self.clip):
+            if tower is not None:
+                for p in tower.parameters():
+                    p.requires_grad = False  # clip_whisper_model.py:873, 893
+
+        # dims as the reference derives them (:216, :247, :1148-1157); defaults for an absent modality (:223, :254)
+        self.audio_dim = audio_dim or (self.whisper.config.d_model if self.whisper is not None else 1024)
+        self.video_dim = video_dim or (self.clip.config.hidden_size if self.clip is not None else 768)
+        self.llm_dim = self._get_llm_dim()
+        self._setup_projections()
+
+    # ------------------------------------------------------------------ construction helpers
+    def _load_llm(self, llm_path):
+        from transformers import AutoModelForCausalLM, AutoTokenizer
+
+        tok = AutoTokenizer.from_pretrained(llm_path)
+        if tok.pad_token is None:
+            tok.pad_token = tok.eos_token  # clip_whisper_model.py:955-959
+        llm = AutoModelForCausalLM.from_pretrained(llm_path, torch_dtype=self.dtype).to(self.device)
+        return tok, llm
+
+    def _load_tower(self, cls_name, path):
+        import transformers
+
+        return getattr(transformers, cls_name).from_pretrained(path).to(self.device).eval()
+
+    def _get_llm_dim(self):
+        return self.llm.get_input_embeddings().weight.shape[1]  # clip_whisper_model.py:1148-1157
+
+    def _setup_projections(self):
+        """Both connectors are always created (clip_whisper_model.py:1159-1190); with stride-k stacking the input
+        width is k * tower width."""
+        self.audio_connector = create_modality_connector(
+            connector_type=self.connector_type, input_dim=self.audio_dim * self.audio_stride,
+            output_dim=self.llm_dim, device=self.device, dtype=self.dtype, max_seq_len=self.max_seq_len)
+        self.video_connector = create_modality_connector(
+            connector_type=self.connector_type, input_dim=self.video_dim * self.video_stride,
+            output_dim=self.llm_dim, device=self.device, dtype=self.dtype, max_seq_len=self.max_seq_len)
+
+    def _plan(self) -> FusePlan:
+        return FusePlan(modality=self.modality, fusion=self.fusion, fusion_scale=self.fusion_scale,
+                        max_seq_len=self.max_seq_len, audio_stride=self.audio_stride,
+                        video_stride=self.video_stride, mask_mode=self.mask_mode, label_mode=self.label_mode)
+
+    # ------------------------------------------------------------------ towers (untouched PyTorch)
+    def _whisper_features(self, audio, attention_mask=None):
+        """Input checks and tower call of encode_audio (clip_whisper_model.py:1067-1103)."""
+        if audio is None:
+            raise ValueError("Audio input cannot be None")
+        if len(audio.shape) != 2 and (len(audio.shape) != 3 or audio.shape[1] != 80):
+            raise ValueError("Audio input should have shape [batch_size, sequence_length] or "
+                             f"[batch_size, 80, time_steps], but got {audio.shape}")
+        if len(audio.shape) == 3 and attention_mask is None:
+            attention_mask = torch.ones((audio.shape[0], audio.shape[2]), dtype=torch.long, device=audio.device)
+        whisper_dtype = next(self.whisper.parameters()).dtype
+        if audio.dtype != whisper_dtype:
+            audio = audio.to(whisper_dtype)
+        with torch.no_grad():
+            out = self.whisper.encoder(audio, attention_mask=attention_mask, output_hidden_states=True,
+                                       return_dict=True)
+        return out.last_hidden_state
+
+    def _clip_cls_features(self, video):
+        """Input checks, tower call and CLS select of encode_video (clip_whisper_model.py:1108-1142).  The CLS rows
+        are returned as a strided VIEW of last_hidden_state; the gather kernel reads them in place."""
+        if len(video.shape) != 5 or video.shape[2] != 3:
+            raise ValueError("Video input should have shape [batch_size, frames, 3, height, width], "
+                             f"but got {video.shape}")
+        B, F = video.shape[0], video.shape[1]
+        flat = video.view(B * F, 3, video.shape[3], video.shape[4])
+        clip_dtype = next(self.clip.parameters()).dtype
+        if flat.dtype != clip_dtype:
+            flat = flat.to(clip_dtype)
+        with torch.no_grad():
+            hidden = self.clip(flat, return_dict=True).last_hidden_state  # [B*F, 1+Np, Dv]
+        if not hidden.is_contiguous():
+            hidden = hidden.contiguous()
+        n1, Dv = hidden.shape[1], hidden.shape[2]
+        return torch.as_strided(hidden, (B, F, Dv), (F * n1 * Dv, n1 * Dv, 1))
+
+    def encode_audio(self, audio, attention_mask=None):
+        """Whisper encoder -> audio connector: [B, Ta, H] (clip_whisper_model.py:1067-1106).  Stand-alone use
+        requires audio_stride == 1 (the connector input is then the tower width, as in the reference)."""
+        feats = self._whisper_features(audio, attention_mask)
+        if self.audio_stride != 1:
+            feats = _stack_view(feats, self.audio_stride)
+        return self.audio_connector(feats)
+
+    def encode_video(self, video, attention_mask=None):
+        """CLIP -> CLS rows -> video connector: [B, F, H] (clip_whisper_model.py:1108-1146)."""
+        feats = self._clip_cls_features(video)
+        if self.video_stride != 1:
+            feats = _stack_view(feats.contiguous(), self.video_stride)
+        return self.video_connector(feats)
+
+    # ------------------------------------------------------------------ the hot path
+    def _prompt_ids(self, prompt):
+        """Token ids of the prompt, capped at 32 (clip_whisper_model.py:464-482)."""
+        if prompt is None:
+            return None
+        if isinstance(prompt, str) or (isinstance(prompt, (list, tuple)) and prompt and isinstance(prompt[0], str)):
+            ids = self.tokenizer(prompt, return_tensors="pt", padding=True, truncation=True,
+                                 max_length=MAX_PROMPT_LEN).input_ids
+        else:
+            ids = prompt
+        ids = ids.to(self.device)
+        return ids[:, :MAX_PROMPT_LEN]
+
+    def _embed_prompt(self, prompt):
+        ids = self._prompt_ids(prompt)
+        return None if ids is None else self.llm.get_input_embeddings()(ids)
+
+    def _fused(self, audio, video, prompt=None, labels=None, input_ids=None, placeholder_id=-1,
+               audio_lengths=None, video_lengths=None):
+        a = v = None
+        if self.modality in ("audio", "both") and audio is not None:
+            a = self._whisper_features(audio)
+        if self.modality in ("video", "both") and video is not None:
+            v = self._clip_cls_features(video)
+        if a is None and v is None:
+            raise ValueError("No valid inputs provided - both audio and video are None")
+        llm_dtype = next(self.llm.parameters()).dtype  # clip_whisper_model.py:454
+        table = self.llm.get_input_embeddings().weight
+        pad_id = self.tokenizer.pad_token_id if self.tokenizer is not None else 0
+        return fused_connector(
+            a, v, self.audio_connector.linear.weight, self.audio_connector.linear.bias,
+            self.video_connector.linear.weight, self.video_connector.linear.bias, self._plan(),
+            input_ids=input_ids, prompt_ids=self._prompt_ids(prompt), placeholder_id=placeholder_id,
+            embed_table=table.detach(), labels=labels, pad_id=pad_id, out_dtype=llm_dtype,
+            audio_lengths=audio_lengths, video_lengths=video_lengths)
+
+    def encode(self, audio=None, video=None, prompt=None, input_ids=None, placeholder_id=-1,
+               audio_lengths=None, video_lengths=None):
+        """(inputs_embeds [B, P+T, H] in the LLM dtype, attention_mask int64 [B, P+T]) -- clip_whisper_model.py:407-462.
+
+        Extension: `input_ids` containing `placeholder_id` runs selects the splice positions instead of the
+        reference's fixed `[prompt | AV]` layout."""
+        emb, mask, _ = self._fused(audio, video, prompt, None, input_ids, placeholder_id, audio_lengths,
+                                   video_lengths)
+        return emb, mask
+
+    def forward(self, audio=None, video=None, prompt=None, labels=None, return_loss=True, input_ids=None,
+                placeholder_id=-1, audio_lengths=None, video_lengths=None):
+        """clip_whisper_model.py:489-619."""
+        use_labels = labels is not None and return_loss
+        if use_labels:
+            labels = self._coerce_labels(labels)
+        # eval rule (pad -> -100, truncate / right-pad) is produced by the splice kernel
+        emb, mask, lab = self._fused(audio, video, prompt, labels if use_labels else None, input_ids,
+                                     placeholder_id, audio_lengths, video_lengths)
+        if use_labels and self.training and labels.shape[1] != emb.shape[1]:
+            # training branch (:577-585): sequence is resampled to the label length, labels only get pad -> -100
+            emb = adaptive_projection(emb, labels.shape[1])
+            mask = adapt_mask(mask, labels.shape[1])
+            lab = labels.clone()
+            lab[lab == self.tokenizer.pad_token_id] = -100
+        if use_labels:
+            outputs = self.llm(inputs_embeds=emb, attention_mask=mask, labels=lab, return_dict=True)
+        else:
+            outputs = self.llm(inputs_embeds=emb, attention_mask=mask, return_dict=True)
+        if return_loss:
+            return {"loss": outputs.loss, "logits": outputs.logits}
+        return {"logits": outputs.logits}
+
+    def _coerce_labels(self, labels):
+        """List -> tensor coercions of clip_whisper_model.py:505-567 (strings go through the tokenizer)."""
+        if isinstance(labels, list):
+            if all(isinstance(x, torch.Tensor) for x in labels):
+                labels = torch.stack(labels)
+            elif all(isinstance(x, str) for x in labels):
+                labels = self.tokenizer(labels, return_tensors="pt", padding=True, truncation=True,
+                                        max_length=self.max_seq_len).input_ids
+            else:
+                labels = torch.tensor(labels)
+        if not isinstance(labels, torch.Tensor):
+            raise TypeError(f"labels must be a tensor or a list, got {type(labels).__name__}")
+        return labels.to(self.device)
+
+    @torch.no_grad()
+    def generate(self, audio=None, video=None, prompt=None, pixel_values=None, max_new_tokens=100, do_sample=False,
+                 temperature=1.0, top_p=0.9, max_length=None):
+        """clip_whisper_model.py:1240-1348: modality follows the inputs that are present, then llm.generate."""
+        if video is None and pixel_values is not None:
+            video = pixel_values
+        if max_new_tokens is None:
+            max_new_tokens = max_length if max_length is not None else 100
+        original = self.modality
+        if audio is not None and video is not None:
+            self.modality = "both"
+        elif audio is not None:
+            self.modality = "audio"
+        elif video is not None:
+            self.modality = "video"
+        try:
+            emb, mask = self.encode(audio, video, prompt)
+        finally:
+            self.modality = original
+        return self.llm.generate(inputs_embeds=emb, attention_mask=mask, max_new_tokens=max_new_tokens,
+                                 do_sample=do_sample, temperature=temperature, top_p=top_p)
+
+    # ------------------------------------------------------------------ checkpoint compatibility
+    def save_connectors(self, out_dir):
+        """audio_connector.pt / video_connector.pt with the reference's keys (clip_whisper_model.py:745-746)."""
+        import os
+
+        os.makedirs(out_dir, exist_ok=True)
+        torch.save(self.audio_connector.state_dict(), os.path.join(out_dir, "audio_connector.pt"))
+        torch.save(self.video_connector.state_dict(), os.path.join(out_dir, "video_connector.pt"))
+
+    def load_connectors(self, src_dir):
+        import os
+
+        for name in ("audio_connector", "video_connector"):
+            sd = torch.load(os.path.join(src_dir, f"{name}.pt"), map_location=self.device)
+            getattr(self, name).load_state_dict({k: v.float() for k, v in sd.items()})
+        logging.info("loaded connector weights from %s", src_dir)
+
+
+def _stack_view(feats: torch.Tensor, k: int) -> torch.Tensor:
+    """[B, T, D] -> [B, T // k, k*D] (frames k*j .. k*j+k-1 side by side); T must divide by k for the free view."""
+    B, T, D = feats.shape
+    if T % k:
+        raise ValueError(f"{T} frames do not divide by stride {k}; use encode() (the gather pads the ragged tail)")
+    return feats.reshape(B, T // k, k * D)

@@ -1,0 +1,331 @@
+"""Host-side orchestration of the connector kernels (gather -> projector GEMM -> splice, and the backward).
+
+Everything numeric happens inside libavconnector_b200.so (sm_100a CUDA); torch is used for device memory,
+streams and autograd bookkeeping only.  There is no eager-PyTorch or CPU fallback: inputs that are not on an
+sm_100 device raise.
+
+Reference semantics replaced (paths relative to /root/reference/src/clip_whisper/models/):
+  modality_connector.py:16-20,43-44     connector = cast + nn.Linear
+  clip_whisper_model.py:320-374,424-434  pad/truncate AFTER projection + weighted-sum fusion
+  clip_whisper_model.py:448-451,460      prompt-embedding concat + int64 ones mask
+  clip_whisper_model.py:569-570,586-598  pad -> -100, truncate / right-pad labels
+  clip_whisper_model.py:1141-1142        CLS-row select (folded into the gather through the frame stride)
+The weighted sum after two projections is computed as ONE GEMM over [a_j ; v_j] with
+W = [sa*Wa | sv*Wv] and bias sa*ba*1[audio token] + sv*bv*1[video token].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+MAX_PROMPT_LEN = 32  # clip_whisper_model.py:469
+_SUPPORTED_OUT = (torch.float32, torch.bfloat16)
+
+
+@dataclass(frozen=True)
+class FusePlan:
+    """Connector knobs.  Defaults = reference behaviour (index-aligned, k=1, sum fusion, ones mask)."""
+    modality: str = "both"        # audio | video | both                 (configs/clip_whisper.yaml:21)
+    fusion: str = "sum"           # sum (clip_whisper_model.py:434) | concat (new)
+    fusion_scale: float = 0.5     # configs/clip_whisper.yaml:30
+    max_seq_len: int = 256        # caps fused tokens in `both` mode only  (clip_whisper_model.py:427)
+    audio_stride: int = 1         # k_a frames stacked per token (new; 1 = reference)
+    video_stride: int = 1         # k_v
+    mask_mode: int = 0            # 0 all ones (clip_whisper_model.py:460) | 1 valid tokens only
+    label_mode: int = 0           # 0 reference eval rule | 1 also -100 on placeholders / pad ids
+
+    def __post_init__(self):
+        if self.modality not in ("audio", "video", "both"):
+            raise ValueError(f"modality must be audio|video|both, got {self.modality!r}")
+        if self.fusion not in ("sum", "concat"):
+            raise ValueError(f"fusion must be sum|concat, got {self.fusion!r}")
+        if self.audio_stride < 1 or self.video_stride < 1:
+            raise ValueError("strides must be >= 1")
+
+    def scales(self, use_a: bool, use_v: bool) -> Tuple[float, float]:
+        if use_a and use_v and self.fusion == "sum":
+            return float(self.fusion_scale), float(1 - self.fusion_scale)
+        return 1.0, 1.0
+
+    def tokens(self, Ta: Optional[int], Tv: Optional[int]) -> int:
+        """Fused tokens for Ta audio / Tv video frames: ceil(T/k) per stream, max, capped in `both` mode."""
+        na = -(-Ta // self.audio_stride) if Ta is not None else None
+        nv = -(-Tv // self.video_stride) if Tv is not None else None
+        if na is not None and nv is not None:
+            return min(self.max_seq_len, max(na, nv))
+        return na if na is not None else nv
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise L.ConnectorError(f"{what} is on {t.device}; the B200 connector has no CPU fallback "
+                               "(the reference's cuda-else-cpu default is removed on this path)")
+
+
+def to_bf16_features(x: torch.Tensor) -> torch.Tensor:
+    """[B, T, D] features of any float dtype -> bf16 with D contiguous (cast kernel; strided CLS views allowed)."""
+    _require_cuda(x, "features")
+    if x.dim() != 3:
+        raise ValueError(f"features must be [batch, frames, dim], got {tuple(x.shape)}")
+    if x.dtype == torch.bfloat16 and x.stride(2) == 1:
+        return x
+    if x.dtype != torch.float32 or x.stride(2) != 1:
+        x = x.float().contiguous()
+    B, T, D = x.shape
+    out = torch.empty(B, T, D, dtype=torch.bfloat16, device=x.device)
+    if B * T == 0:
+        return out
+    if x.stride(0) == T * x.stride(1):  # uniform row pitch (dense, or a CLS view of [B*F, 1+Np, D])
+        src2d = torch.as_strided(x, (B * T, D), (x.stride(1), 1))
+        L.pack_weight(src2d, out.view(B * T, D), 1.0)
+    else:
+        for b in range(B):
+            L.pack_weight(x[b], out[b], 1.0)
+    return out
+
+
+def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float]) -> torch.Tensor:
+    """[H, K_s] fp32 master weights -> one bf16 [H, sum K_s] matrix with the fusion scales folded in."""
+    H = weights[0].shape[0]
+    K = sum(w.shape[1] for w in weights)
+    packed = torch.empty(H, K, dtype=torch.bfloat16, device=weights[0].device)
+    col = 0
+    for w, s in zip(weights, scales):
+        if w.dtype != torch.float32 or w.stride(1) != 1:
+            raise ValueError("projector master weights must be fp32 with contiguous columns")
+        L.pack_weight(w, packed[:, col:col + w.shape[1]], s)
+        col += w.shape[1]
+    return packed
+
+
+def _as_int32(x, device) -> Optional[torch.Tensor]:
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).contiguous()
+    return torch.tensor(list(x), dtype=torch.int32, device=device)
+
+
+class _LinearProjectFn(torch.autograd.Function):
+    """y = x . W^T + b on the tcgen05 projector GEMM (one modality; SimpleModalityConnector._forward_impl)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_dtype):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError(
+                "gradient w.r.t. connector inputs (unfrozen towers) is not produced by the B200 path; "
+                "the reference trains with freeze_encoders=True (configs/clip_whisper.yaml:28)")
+        xb = to_bf16_features(x if x.dim() == 3 else x.unsqueeze(0))
+        B, T, D = xb.shape
+        H = weight.shape[0]
+        wp = pack_projector([weight], [1.0])
+        y = torch.empty(B, T, H, dtype=out_dtype, device=x.device)
+        if B * T:
+            L.proj_fwd([xb], [wp], y, bias0=bias)
+        ctx.save_for_backward(xb)
+        ctx.shape = (H, D)
+        ctx.squeeze = x.dim() == 2
+        return y[0] if ctx.squeeze else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xb,) = ctx.saved_tensors
+        H, D = ctx.shape
+        if ctx.squeeze:
+            dy = dy.unsqueeze(0)
+        dyb = to_bf16_features(dy)
+        dw = torch.empty(H, D, dtype=torch.float32, device=dy.device)
+        db = torch.empty(H, dtype=torch.float32, device=dy.device)
+        if xb.shape[0] * xb.shape[1]:
+            L.proj_bwd_dw(dyb, [xb], [dw], [1.0])
+            L.colsum(dyb, db, None, L.colsum_workspace(H, dy.device))
+        else:
+            dw.zero_()
+            db.zero_()
+        return None, dw, db, None
+
+
+def linear_project(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    if out_dtype not in _SUPPORTED_OUT:
+        raise L.ConnectorError(f"connector output dtype {out_dtype} unsupported on the B200 path (fp32 or bf16)")
+    _require_cuda(x, "connector input")
+    return _LinearProjectFn.apply(x, weight, bias, out_dtype)
+
+
+class _FusedConnectorFn(torch.autograd.Function):
+    """gather -> projector GEMM -> splice (+ masks); backward: splice-bwd -> dW GEMM + bias column sums."""
+
+    @staticmethod
+    def forward(ctx, wa, ba, wv, bv, st):
+        dev = st["device"]
+        audio, video = st["audio"], st["video"]
+        plan: FusePlan = st["plan"]
+        use_a, use_v = audio is not None, video is not None
+        sa, sv = plan.scales(use_a, use_v)
+        B, N, M = st["batch"], st["ntok"], st["rows"]
+        H = (wa if use_a else wv).shape[0]
+        ka, kv = plan.audio_stride, plan.video_stride
+        Ka = ka * audio.shape[2] if use_a else 0
+        Kv = kv * video.shape[2] if use_v else 0
+        if use_a and wa.shape[1] != Ka:
+            raise ValueError(f"audio connector expects input_dim {wa.shape[1]} but stacked audio width is {Ka}")
+        if use_v and wv.shape[1] != Kv:
+            raise ValueError(f"video connector expects input_dim {wv.shape[1]} but stacked video width is {Kv}")
+        K = Ka + Kv
+        # 1. gather (align + stack + concat) into the packed A matrix
+        A = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+        flags = torch.empty(M, dtype=torch.uint8, device=dev)
+        if M:
+            L.gather_fwd(audio, video, ka, kv, B, N, A, flags, st["tok_offset"], st["audio_valid"], st["video_valid"])
+        # 2. projector: one GEMM over [a ; v]
+        ws = ([wa] if use_a else []) + ([wv] if use_v else [])
+        wp = pack_projector(ws, ([sa] if use_a else []) + ([sv] if use_v else []))
+        out_dtype = st["out_dtype"]
+        Y = torch.empty(M, H, dtype=out_dtype, device=dev)
+        if use_a and use_v:
+            b0, b1, s0, s1 = ba, bv, sa, sv
+        elif use_a:
+            b0, b1, s0, s1 = ba, None, sa, 0.0
+        else:  # video only: its "present" flag is bit 1
+            b0, b1, s0, s1 = None, bv, 0.0, sv
+        if M:
+            L.proj_fwd([A], [wp], Y, bias0=b0, bias1=b1, bias_scale0=s0, bias_scale1=s1, row_flags=flags)
+        # 3. splice into the LLM input-embedding sequence + masks
+        ids = st["input_ids"]
+        S = ids.shape[1]
+        emb = torch.empty(B, S, H, dtype=out_dtype, device=dev)
+        mask = torch.empty(B, S, dtype=torch.int64, device=dev)
+        want_labels = st["labels"] is not None or plan.label_mode == 1
+        labels_out = torch.empty(B, S, dtype=torch.int64, device=dev) if want_labels else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        sp = L.make_splice(ids, st["placeholder_id"], st["pad_id"], H, tokens_per_sample=N,
+                           tok_offset=st["tok_offset"], embed_table=st["embed_table"], attention_mask=mask,
+                           mask_mode=plan.mask_mode, label_mode=plan.label_mode, labels_in=st["labels"],
+                           labels_out=labels_out, status=status, elem_size=4 if out_dtype == torch.float32 else 2)
+        L.splice_fwd(sp, Y if M else None, emb)
+        ctx.save_for_backward(A, flags)
+        ctx.sp = sp
+        ctx.meta = (use_a, use_v, sa, sv, Ka, Kv, H, M, out_dtype)
+        st["status"] = status
+        st["row_flags"] = flags
+        ctx.mark_non_differentiable(mask)
+        if labels_out is not None:
+            ctx.mark_non_differentiable(labels_out)
+            return emb, mask, labels_out
+        return emb, mask
+
+    @staticmethod
+    def backward(ctx, d_emb, *unused):
+        A, flags = ctx.saved_tensors
+        use_a, use_v, sa, sv, Ka, Kv, H, M, out_dtype = ctx.meta
+        dev = d_emb.device
+        if d_emb.dtype != out_dtype or not d_emb.is_contiguous():
+            d_emb = d_emb.to(out_dtype).contiguous()
+        dwa = torch.empty(H, Ka, dtype=torch.float32, device=dev) if use_a else None
+        dwv = torch.empty(H, Kv, dtype=torch.float32, device=dev) if use_v else None
+        dba = torch.empty(H, dtype=torch.float32, device=dev) if use_a else None
+        dbv = torch.empty(H, dtype=torch.float32, device=dev) if use_v else None
+        if M == 0:
+            for t in (dwa, dwv, dba, dbv):
+                if t is not None:
+                    t.zero_()
+            return dwa, dba, dwv, dbv, None
+        dY = torch.empty(M, H, dtype=out_dtype, device=dev)
+        L.splice_bwd(ctx.sp, d_emb, dY)
+        if out_dtype == torch.float32:
+            dYb = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+            L.pack_weight(dY, dYb, 1.0)
+            dY = dYb
+        xs, dws, al = [], [], []
+        if use_a:
+            xs.append(A[:, :Ka]); dws.append(dwa); al.append(sa)
+        if use_v:
+            xs.append(A[:, Ka:]); dws.append(dwv); al.append(sv)
+        L.proj_bwd_dw(dY, xs, dws, al)
+        ws = L.colsum_workspace(H, dev)
+        # flag bit0 = audio token present, bit1 = video token present
+        L.colsum(dY, dba, dbv, ws, row_flags=flags, alpha0=sa, alpha1=sv)
+        return dwa, dba, dwv, dbv, None
+
+
+def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor], wa, ba, wv, bv, plan: FusePlan, *,
+                    input_ids: Optional[torch.Tensor] = None, prompt_ids: Optional[torch.Tensor] = None,
+                    placeholder_id: int = -1, embed_table: Optional[torch.Tensor] = None,
+                    labels: Optional[torch.Tensor] = None, pad_id: int = 0, out_dtype: torch.dtype = torch.bfloat16,
+                    audio_lengths=None, video_lengths=None, check: bool = False):
+    """Tower features -> (inputs_embeds [B, S, H], attention_mask int64 [B, S], labels int64 [B, S] | None).
+
+    audio [B, Ta, Da] / video [B, Tv, Dv] (video may be a strided CLS view of CLIP's last_hidden_state).
+    Layout: `input_ids` with `placeholder_id` runs marks where the AV tokens go; without it the reference layout
+    `[prompt_ids[:, :32] | AV tokens]` is built (clip_whisper_model.py:448-451).
+    audio_lengths / video_lengths (host ints or int32 tensors, valid frames per sample) switch to ragged packing:
+    sample b contributes ntok_b = tokens(len_a[b], len_v[b]) rows and needs exactly ntok_b placeholders.
+    """
+    if out_dtype not in _SUPPORTED_OUT:
+        raise L.ConnectorError(f"LLM dtype {out_dtype} unsupported on the B200 path (fp32 or bf16)")
+    use_a = plan.modality in ("audio", "both") and audio is not None
+    use_v = plan.modality in ("video", "both") and video is not None
+    if not (use_a or use_v):
+        raise ValueError("No valid inputs provided - both audio and video are None")  # clip_whisper_model.py:445
+    a = to_bf16_features(audio) if use_a else None
+    v = to_bf16_features(video) if use_v else None
+    dev = (a if use_a else v).device
+    B = (a if use_a else v).shape[0]
+    if use_a and use_v and a.shape[0] != v.shape[0]:
+        raise ValueError("audio and video batch sizes differ")
+    N = plan.tokens(a.shape[1] if use_a else None, v.shape[1] if use_v else None)
+    tok_offset = audio_valid = video_valid = None
+    rows = B * N
+    ragged = audio_lengths is not None or video_lengths is not None
+    if ragged:
+        la = None if not use_a or audio_lengths is None else [min(int(x), a.shape[1]) for x in _host_list(audio_lengths)]
+        lv = None if not use_v or video_lengths is None else [min(int(x), v.shape[1]) for x in _host_list(video_lengths)]
+        counts = []
+        for b in range(B):
+            counts.append(plan.tokens(la[b] if la is not None else (a.shape[1] if use_a else None),
+                                      lv[b] if lv is not None else (v.shape[1] if use_v else None)))
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        rows = offs[-1]
+        tok_offset = torch.tensor(offs, dtype=torch.int32, device=dev)
+        audio_valid = _as_int32(la, dev)
+        video_valid = _as_int32(lv, dev)
+    if input_ids is None:
+        ph = torch.full((B, N), placeholder_id, dtype=torch.int64, device=dev)
+        if ragged:
+            raise ValueError("ragged lengths need explicit input_ids with one placeholder per fused token")
+        if prompt_ids is not None:
+            _require_cuda(prompt_ids, "prompt ids")
+            input_ids = torch.cat([prompt_ids[:, :MAX_PROMPT_LEN].to(torch.int64), ph], dim=1)
+        else:
+            input_ids = ph
+    else:
+        _require_cuda(input_ids, "input_ids")
+        input_ids = input_ids.to(torch.int64).contiguous()
+    if embed_table is not None:
+        if embed_table.dtype != out_dtype or not embed_table.is_contiguous():
+            raise ValueError(f"embedding table must be contiguous {out_dtype} (the LLM dtype)")
+    if labels is not None:
+        _require_cuda(labels, "labels")
+        labels = labels.to(torch.int64).contiguous()
+    st = dict(device=dev, audio=a, video=v, plan=plan, batch=B, ntok=N, rows=rows, tok_offset=tok_offset,
+              audio_valid=audio_valid, video_valid=video_valid, out_dtype=out_dtype, input_ids=input_ids,
+              placeholder_id=placeholder_id, pad_id=pad_id, embed_table=embed_table, labels=labels)
+    dummy = torch.zeros(0, device=dev)
+    out = _FusedConnectorFn.apply(wa if use_a else dummy, ba if use_a else dummy, wv if use_v else dummy,
+                                  bv if use_v else dummy, st)
+    if check and int(st["status"].item()) != 0:
+        raise L.ConnectorError("placeholder count does not match the number of fused tokens for some sample")
+    emb, mask = out[0], out[1]
+    return emb, mask, (out[2] if len(out) > 2 else None)
+
+
+def _host_list(x):
+    if isinstance(x, torch.Tensor):
+        return x.tolist()
+    return list(x)

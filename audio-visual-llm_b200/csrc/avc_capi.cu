@@ -176,8 +176,8 @@ int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t batch, 
 }
 
 int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat* y, int32_t y_is_fp32,
-                 const float* bias0, const float* bias1, const uint8_t* row_flags, int32_t flag_rows0,
-                 int32_t flag_rows1, int32_t act, void* stream) {
+                 const float* bias0, const float* bias1, float bias_scale0, float bias_scale1,
+                 const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, int32_t act, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (nseg < 1 || nseg > 2) return fail(AVC_ERR_INVALID, "proj_fwd: nseg must be 1 or 2");
@@ -219,6 +219,8 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   g.flag_rows0 = flag_rows0;
   g.flag_rows1 = flag_rows1;
   g.alpha[0] = g.alpha[1] = 1.f;
+  g.bias_scale[0] = bias_scale0;
+  g.bias_scale[1] = bias_scale1;
   g.act = act;
   if ((bias0 && (reinterpret_cast<uintptr_t>(bias0) & 15)) || (bias1 && (reinterpret_cast<uintptr_t>(bias1) & 15)))
     return fail(AVC_ERR_INVALID, "proj_fwd: bias pointers must be 16-byte aligned");
@@ -324,7 +326,9 @@ static int fill_splice(const avc_splice* s, avc::SpliceArgs* k) {
   k->pad_id = s->pad_id;
   k->batch = s->batch;
   k->seq = s->seq;
-  k->row_bytes = s->hidden * 2;
+  if (s->elem_size != 0 && s->elem_size != 2 && s->elem_size != 4)
+    return fail(AVC_ERR_INVALID, "splice: elem_size must be 2 (bf16) or 4 (fp32)");
+  k->row_bytes = s->hidden * (s->elem_size == 4 ? 4 : 2);
   k->tok_offset = s->tok_offset;
   k->tokens_per_sample = s->tokens_per_sample;
   k->embed_table = static_cast<const uint8_t*>(s->embed_table);
@@ -364,6 +368,32 @@ int avc_splice_bwd(const avc_splice* s, const void* d_inputs_embeds, void* dy, v
   k.labels_out = nullptr;
   cudaError_t e = avc::launch_splice_bwd(k, di.num_sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "splice_bwd launch");
+  return AVC_OK;
+}
+
+int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_t batch, int32_t src_rows, int32_t dst_rows,
+                     int32_t hidden, const int32_t* row_ptr, const int32_t* col_idx, const float* weight,
+                     void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (x == nullptr || out == nullptr || row_ptr == nullptr || col_idx == nullptr || weight == nullptr)
+    return fail(AVC_ERR_INVALID, "row_resample: null pointer");
+  if (elem_size != 2 && elem_size != 4) return fail(AVC_ERR_INVALID, "row_resample: elem_size must be 2 or 4");
+  if (batch < 0 || src_rows <= 0 || dst_rows < 0 || hidden <= 0) return fail(AVC_ERR_INVALID, "row_resample: bad extents");
+  avc::ResampleArgs r;
+  memset(&r, 0, sizeof(r));
+  r.x = static_cast<const uint8_t*>(x);
+  r.out = static_cast<uint8_t*>(out);
+  r.elem_size = elem_size;
+  r.batch = batch;
+  r.src_rows = src_rows;
+  r.dst_rows = dst_rows;
+  r.hidden = hidden;
+  r.row_ptr = row_ptr;
+  r.col = col_idx;
+  r.weight = weight;
+  cudaError_t e = avc::launch_row_resample(r, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "row_resample launch");
   return AVC_OK;
 }
 

@@ -41,6 +41,7 @@ struct GemmArgs {
   int flag_rows0;            // analytic: bit0 = row < flag_rows0
   int flag_rows1;            // analytic: bit1 = row < flag_rows1
   float alpha[2];            // NT: output scale per segment
+  float bias_scale[2];       // TN: bias multipliers (fusion_scale folded into the bias)
   int act;                   // 0 = identity, 1 = GELU (erf form)
 };
 
@@ -117,5 +118,19 @@ struct ColsumArgs {
 };
 size_t colsum_workspace_bytes(int cols);
 cudaError_t launch_colsum(const ColsumArgs& args, cudaStream_t stream);
+
+// Row resampling (sparse row mixing): out[b, i, :] = sum_t weight[t] * x[b, col[t], :], t in CSR row i.
+// Train-time length adaptation of the reference (adaptive avg-pool / linear interpolation,
+// clip_whisper_model.py:621-676) and its transpose for the backward.
+struct ResampleArgs {
+  const uint8_t* x;   // [batch, src_rows, hidden]
+  uint8_t* out;       // [batch, dst_rows, hidden]
+  int elem_size;      // 2 = bf16, 4 = fp32
+  int batch, src_rows, dst_rows, hidden;
+  const int32_t* row_ptr;  // [dst_rows + 1]
+  const int32_t* col;      // [nnz] source row index
+  const float* weight;     // [nnz]
+};
+cudaError_t launch_row_resample(const ResampleArgs& args, cudaStream_t stream);
 
 }  // namespace avc

@@ -90,7 +90,60 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_final_kernel(const __grid_c
   if (a.out1 != nullptr) a.out1[col] = a.alpha1 * s1;
 }
 
+// out[b, i, :] = sum_{t in [row_ptr[i], row_ptr[i+1])} weight[t] * x[b, col[t], :]   (fp32 accumulate)
+template <bool F32>
+__global__ void __launch_bounds__(128) row_resample_kernel(const __grid_constant__ ResampleArgs a) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int t0 = __ldg(a.row_ptr + i), t1 = __ldg(a.row_ptr + i + 1);
+  constexpr int EPV = F32 ? 4 : 8;  // elements per 16-byte vector
+  const int64_t row_bytes = static_cast<int64_t>(a.hidden) * (F32 ? 4 : 2);
+  const uint8_t* xb = a.x + static_cast<int64_t>(b) * a.src_rows * row_bytes;
+  uint8_t* ob = a.out + (static_cast<int64_t>(b) * a.dst_rows + i) * row_bytes;
+  for (int v = threadIdx.x; v < a.hidden / EPV; v += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      const float w = __ldg(a.weight + t);
+      const int4 q = ld_nc_v4(xb + static_cast<int64_t>(__ldg(a.col + t)) * row_bytes + static_cast<int64_t>(v) * 16);
+      if (F32) {
+        acc[0] = fmaf(w, __int_as_float(q.x), acc[0]);
+        acc[1] = fmaf(w, __int_as_float(q.y), acc[1]);
+        acc[2] = fmaf(w, __int_as_float(q.z), acc[2]);
+        acc[3] = fmaf(w, __int_as_float(q.w), acc[3]);
+      } else {
+        const uint32_t u[4] = {static_cast<uint32_t>(q.x), static_cast<uint32_t>(q.y),
+                               static_cast<uint32_t>(q.z), static_cast<uint32_t>(q.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e + 0] = fmaf(w, __uint_as_float(u[e] << 16), acc[2 * e + 0]);
+          acc[2 * e + 1] = fmaf(w, __uint_as_float(u[e] & 0xffff0000u), acc[2 * e + 1]);
+        }
+      }
+    }
+    int4 o;
+    if (F32) {
+      o = make_int4(__float_as_int(acc[0]), __float_as_int(acc[1]), __float_as_int(acc[2]), __float_as_int(acc[3]));
+    } else {
+      o = make_int4(static_cast<int>(pack_bf16x2(acc[0], acc[1])), static_cast<int>(pack_bf16x2(acc[2], acc[3])),
+                    static_cast<int>(pack_bf16x2(acc[4], acc[5])), static_cast<int>(pack_bf16x2(acc[6], acc[7])));
+    }
+    st_na_v4(ob + static_cast<int64_t>(v) * 16, o);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_row_resample(const ResampleArgs& a, cudaStream_t stream) {
+  if (a.batch <= 0 || a.dst_rows <= 0) return cudaSuccess;
+  const int epv = a.elem_size == 4 ? 4 : 8;
+  if (a.hidden % epv != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
+    return cudaErrorMisalignedAddress;
+  if (a.batch > 65535) return cudaErrorInvalidValue;
+  dim3 grid(a.dst_rows, a.batch);
+  if (a.elem_size == 4) row_resample_kernel<true><<<grid, 128, 0, stream>>>(a);
+  else row_resample_kernel<false><<<grid, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int64_t dst_ld,
                                int64_t rows, int64_t cols, float alpha, cudaStream_t stream) {

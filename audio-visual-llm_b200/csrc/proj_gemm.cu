@@ -202,12 +202,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (args.row_flags != nullptr) {
           if (my_row < args.d_rows) {
             const uint8_t fl = args.row_flags[static_cast<int64_t>(out_batch) * args.d_rows + my_row];
-            f0 = (fl & 1) ? 1.f : 0.f;
-            f1 = (fl & 2) ? 1.f : 0.f;
+            f0 = (fl & 1) ? args.bias_scale[0] : 0.f;
+            f1 = (fl & 2) ? args.bias_scale[1] : 0.f;
           }
         } else {
-          f0 = my_row < args.flag_rows0 ? 1.f : 0.f;
-          f1 = my_row < args.flag_rows1 ? 1.f : 0.f;
+          f0 = my_row < args.flag_rows0 ? args.bias_scale[0] : 0.f;
+          f1 = my_row < args.flag_rows1 ? args.bias_scale[1] : 0.f;
         }
         if (args.bias0 == nullptr) f0 = 0.f;
         if (args.bias1 == nullptr) f1 = 0.f;
@@ -249,11 +249,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             if (n < ncols) {
               if (f0 != 0.f) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias0 + n));
-                xg[0] += b.x; xg[1] += b.y; xg[2] += b.z; xg[3] += b.w;
+                xg[0] = fmaf(f0, b.x, xg[0]); xg[1] = fmaf(f0, b.y, xg[1]);
+                xg[2] = fmaf(f0, b.z, xg[2]); xg[3] = fmaf(f0, b.w, xg[3]);
               }
               if (f1 != 0.f) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias1 + n));
-                xg[0] += b.x; xg[1] += b.y; xg[2] += b.z; xg[3] += b.w;
+                xg[0] = fmaf(f1, b.x, xg[0]); xg[1] = fmaf(f1, b.y, xg[1]);
+                xg[2] = fmaf(f1, b.z, xg[2]); xg[3] = fmaf(f1, b.w, xg[3]);
               }
             }
             if (args.act == 1) {

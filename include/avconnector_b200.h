@@ -77,14 +77,14 @@ AVC_API int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t
                    void* stream);
 
 /* ---- projector forward (tensor-core bound, tcgen05 + TMEM + TMA) -------------------------------
- * Y[b, r, :] = act( sum_s A_s[b, r, :] . W_s^T  + flag0(b,r) * bias0 + flag1(b,r) * bias1 )
+ * Y[b, r, :] = act( sum_s A_s[b, r, :] . W_s^T  + flag0(b,r) * bias_scale0 * bias0 + flag1(b,r) * bias_scale1 * bias1 )
  * flags come from row_flags (packed rows) or, if NULL, flag_i = (r < flag_rows_i).
  * Replaces SimpleModalityConnector.forward x2 + weighted sum (modality_connector.py:43-44,
  * clip_whisper_model.py:434) through W = [fs*Wa | (1-fs)*Wv], bias0 = fs*ba, bias1 = (1-fs)*bv. */
 AVC_API int avc_proj_fwd(int32_t nseg, const avc_mat* a /* [nseg] bf16 */, const avc_mat* w /* [nseg] bf16 [N, K_s] */,
                  const avc_mat* y, int32_t y_is_fp32, const float* bias0, const float* bias1,
-                 const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1,
-                 int32_t act /* 0 none, 1 GELU(erf) */, void* stream);
+                 float bias_scale0, float bias_scale1, const uint8_t* row_flags, int32_t flag_rows0,
+                 int32_t flag_rows1, int32_t act /* 0 none, 1 GELU(erf) */, void* stream);
 
 /* ---- projector backward: weight gradient ------------------------------------------------------
  * dW_s[h, k] = alpha_s * sum_{b, r < x.rows} dY[b, dy_row_base + r, h] * X_s[b, r, k]   (fp32 out)
@@ -121,14 +121,14 @@ typedef struct avc_splice {
   int32_t hidden;             /* H, multiple of 8 */
   int32_t tokens_per_sample;  /* used when tok_offset is NULL */
   const int32_t* tok_offset;  /* [batch+1] or NULL */
-  const void* embed_table;    /* bf16 [vocab, H] or NULL */
+  const void* embed_table;    /* [vocab, H] (elem_size bytes per element) or NULL */
   int64_t vocab;
   int64_t* attention_mask;    /* [batch, seq] or NULL */
   int32_t mask_mode;
   int32_t label_mode;
   const int64_t* labels_in;   /* [batch, label_len] or NULL */
   int32_t label_len;
-  int32_t reserved;
+  int32_t elem_size;          /* bytes per element of y / embed_table / inputs_embeds: 2 (bf16) or 4 (fp32); 0 = 2 */
   int64_t* labels_out;        /* [batch, seq] or NULL */
   int32_t* status;            /* device int32 or NULL */
 } avc_splice;
@@ -138,6 +138,15 @@ AVC_API int avc_splice_fwd(const avc_splice* s, const void* y /* bf16 [M, H] */,
 /* dY[tok_offset[b] + rank(p)] = d_inputs_embeds[b, p] at placeholder positions (autograd of the cat). */
 AVC_API int avc_splice_bwd(const avc_splice* s, const void* d_inputs_embeds, void* dy /* bf16 [M, H] */,
                    void* stream);
+
+/* ---- row resample: out[b, i, :] = sum_{t in CSR row i} weight[t] * x[b, col_idx[t], :] ------------
+ * With the CSR matrix of adaptive average pooling (windows [floor(i*S/L), ceil((i+1)*S/L)), weight 1/len) or
+ * of linear interpolation with align_corners (two taps) this replaces _adaptive_projection
+ * (clip_whisper_model.py:621-676); with the transposed matrix it is that op's backward.
+ * elem_size: 2 = bf16, 4 = fp32 (accumulation is fp32 either way). */
+AVC_API int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_t batch, int32_t src_rows,
+                             int32_t dst_rows, int32_t hidden, const int32_t* row_ptr, const int32_t* col_idx,
+                             const float* weight, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,276 @@
+"""Model-level parity on a B200: the drop-in ClipWhisperModel / ModalityConnector against
+(1) outputs of the executing reference (tests/golden/ref_*.npz) and (2) the CPU oracle for the extensions.
+
+Tolerances (north_star): indices / masks / labels / copied text rows bit-exact; projected embeddings and
+gradients max-relative error <= 1e-2 and cosine >= 0.9999 against the fp32 reference (bf16 operands, fp32
+accumulate)."""
+import ast
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import connector_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+CASES = sorted(p.stem[len("ref_"):] for p in GOLDEN.glob("ref_*.npz") if "cfg1" not in p.stem)
+REL_TOL, COS_TOL = 1e-2, 0.9999
+
+
+def rel_err(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def cosine(got, ref):
+    got, ref = got.detach().double().cpu().flatten(), ref.detach().double().cpu().flatten()
+    return float(torch.dot(got, ref) / (got.norm() * ref.norm()).clamp_min(1e-30))
+
+
+def assert_close(got, ref, what):
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    r, c = rel_err(got, ref), cosine(got, ref)
+    assert r <= REL_TOL and c >= COS_TOL, f"{what}: max-rel {r:.3e}, cosine {c:.6f}"
+
+
+class StubWhisper(nn.Module):
+    def __init__(self, d_model):
+        super().__init__()
+        self.dummy = nn.Parameter(torch.zeros(1))
+        self.config = SimpleNamespace(d_model=d_model)
+        self.features = None
+        outer = self
+
+        class Enc(nn.Module):
+            def forward(self, audio, attention_mask=None, output_hidden_states=True, return_dict=True):
+                return SimpleNamespace(last_hidden_state=outer.features)
+
+        self.encoder = Enc()
+
+
+class StubClip(nn.Module):
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.dummy = nn.Parameter(torch.zeros(1))
+        self.config = SimpleNamespace(hidden_size=hidden_size)
+        self.hidden = None
+
+    def forward(self, flat, return_dict=True):
+        return SimpleNamespace(last_hidden_state=self.hidden)
+
+
+class StubLLM(nn.Module):
+    def __init__(self, table):
+        super().__init__()
+        self.embed = nn.Embedding.from_pretrained(table.clone(), freeze=True)
+        self.calls = []
+        self.upstream = None
+
+    def get_input_embeddings(self):
+        return self.embed
+
+    def forward(self, inputs_embeds=None, attention_mask=None, labels=None, return_dict=True):
+        self.calls.append(dict(inputs_embeds=inputs_embeds, attention_mask=attention_mask, labels=labels))
+        loss = (inputs_embeds.float() * self.upstream.to(inputs_embeds.device)).sum()
+        return SimpleNamespace(loss=loss, logits=inputs_embeds)
+
+
+def build_model(pkg, dev, d, cfg, llm_dtype, Da=32, Dv=16, **kw):
+    table = d["in.embed_table"].to(dev, llm_dtype)
+    m = pkg.ClipWhisperModel(
+        device="cuda:0", modality=cfg["modality"], max_seq_len=cfg["max_seq_len"], fusion_scale=cfg["fs"],
+        _provided_tokenizer=SimpleNamespace(pad_token_id=0), _provided_llm=StubLLM(table).to(dev),
+        _provided_whisper=StubWhisper(Da).to(dev), _provided_clip=StubClip(Dv).to(dev), **kw)
+    sd = {k[len("in."):]: v.to(dev) for k, v in d.items() if "connector.linear" in k}
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    return m
+
+
+def load(name):
+    z = np.load(GOLDEN / f"ref_{name}.npz")
+    d = {k: torch.from_numpy(z[k]) for k in z.files if k != "cfg"}
+    return d, ast.literal_eval(str(z["cfg"]))
+
+
+def drive(m, d, cfg, dev, train):
+    audio = video = None
+    if "in.audio_feats" in d:
+        m.whisper.features = d["in.audio_feats"].to(dev)
+        audio = torch.zeros(2, 80, 4, device=dev)
+    if "in.clip_hidden" in d:
+        m.clip.hidden = d["in.clip_hidden"].to(dev)
+        video = torch.zeros(2, cfg["Tv"], 3, 2, 2, device=dev)
+    m.llm.upstream = d["in.upstream"]
+    m.train(train)
+    prompt = d["in.prompt"].to(dev) if "in.prompt" in d else None
+    res = m(audio=audio, video=video, prompt=prompt, labels=d["in.labels"].to(dev))
+    res["loss"].backward()
+    torch.cuda.synchronize()
+    return m.llm.calls[-1]
+
+
+@pytest.mark.parametrize("llm_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", CASES)
+def test_model_forward_backward_matches_executing_reference(avc, cuda_dev, name, llm_dtype):
+    d, cfg = load(name)
+    m = build_model(avc, cuda_dev, d, cfg, llm_dtype)
+    rec = drive(m, d, cfg, cuda_dev, cfg["train"])
+    emb, ref = rec["inputs_embeds"], d["out.inputs_embeds"]
+    assert emb.dtype == llm_dtype and emb.shape == ref.shape
+    assert_close(emb, ref, "inputs_embeds")
+    P = min(d["in.prompt"].shape[1], 32) if "in.prompt" in d else 0
+    if P and not cfg["train"]:  # copied text rows are exact (in the LLM dtype)
+        assert torch.equal(emb[:, :P].cpu(), ref[:, :P].to(llm_dtype))
+    assert rec["attention_mask"].dtype == torch.int64 and torch.equal(rec["attention_mask"].cpu(), d["out.attention_mask"])
+    assert rec["labels"].dtype == torch.int64 and torch.equal(rec["labels"].cpu(), d["out.labels"])
+    for n in ("audio_connector", "video_connector"):
+        for p in ("weight", "bias"):
+            key = f"out.{n}.linear.{p}.grad"
+            g = getattr(getattr(m, n).linear, p).grad
+            if key in d:
+                assert g is not None and g.dtype == torch.float32
+                assert_close(g, d[key], key)
+            else:
+                assert g is None or float(g.abs().max()) == 0.0
+
+
+def test_state_dict_keys_and_shapes_match_reference(avc, cuda_dev):
+    d, cfg = load("both_prompt_eval")
+    m = build_model(avc, cuda_dev, d, cfg, torch.float32)
+    names = dict(m.named_parameters())
+    for n, shape in [("audio_connector.linear.weight", (48, 32)), ("audio_connector.linear.bias", (48,)),
+                     ("video_connector.linear.weight", (48, 16)), ("video_connector.linear.bias", (48,))]:
+        assert tuple(names[n].shape) == shape and names[n].dtype == torch.float32
+    assert set(m.audio_connector.state_dict()) == {"linear.weight", "linear.bias"}
+
+
+def test_modality_connector_module_fwd_bwd(avc, cuda_dev):
+    """ModalityConnector(input_dim, output_dim, device=)(x) as decode.py:211-221 / encode_audio use it."""
+    g = torch.Generator().manual_seed(5)
+    conn = avc.ModalityConnector(input_dim=64, output_dim=96, device="cuda:0")
+    assert avc.create_modality_connector("simple", 64, 96, device="cuda:0", max_seq_len=7).linear.weight.shape == (96, 64)
+    with torch.no_grad():
+        conn.linear.bias.copy_(torch.randn(96, generator=g))
+    x = torch.randn(3, 50, 64, generator=g)
+    up = torch.randn(3, 50, 96, generator=g)
+    w, b = conn.linear.weight.detach().cpu().clone().requires_grad_(True), conn.linear.bias.detach().cpu().clone().requires_grad_(True)
+    ref = O.reference_connector(x, w, b)
+    (ref * up).sum().backward()
+    y = conn(x.to(cuda_dev))
+    assert y.dtype == torch.float32
+    (y * up.to(cuda_dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(y, ref, "y")
+    assert_close(conn.linear.weight.grad, w.grad, "dW")
+    assert_close(conn.linear.bias.grad, b.grad, "db")
+    with pytest.raises(NotImplementedError):
+        avc.create_modality_connector("qformer", 64, 96)
+
+
+def _rand_params(g, H, Ka, Kv):
+    return (torch.randn(H, Ka, generator=g) / Ka ** 0.5, torch.randn(H, generator=g) * 0.1,
+            torch.randn(H, Kv, generator=g) / Kv ** 0.5, torch.randn(H, generator=g) * 0.1)
+
+
+@pytest.mark.parametrize("fusion", ["concat", "sum"])
+def test_stride_stack_rate_aligned_vs_oracle(avc, cuda_dev, fusion):
+    """cfg2-style: k_a=4 audio + k_v=2 video frames per token (rate-aligned), ragged tails, prompt."""
+    g = torch.Generator().manual_seed(31)
+    B, Ta, Tv, Da, Dv, H, P, V = 3, 50, 23, 64, 32, 128, 6, 40
+    a, v = torch.randn(B, Ta, Da, generator=g), torch.randn(B, Tv, Dv, generator=g)
+    wa, ba, wv, bv = _rand_params(g, H, 4 * Da, 2 * Dv)
+    table = torch.randn(V, H, generator=g)
+    prompt = torch.randint(1, V, (B, P), generator=g)
+    labels = torch.randint(0, V, (B, 9), generator=g)
+    spec = O.ConnectorSpec(fusion=fusion, fusion_scale=0.3, audio_stride=4, video_stride=2, max_seq_len=64)
+    emb_r, mask_r, lab_r, flags_r = O.connector_forward(a, v, wa, ba, wv, bv, spec, prompt_ids=prompt,
+                                                        embed_table=table, labels=labels)
+    N = emb_r.shape[1] - P
+    assert N == 13
+    up = torch.randn(B, P + N, H, generator=g)
+    grads_r = O.connector_grads(a, v, wa, ba, wv, bv, spec, up[:, P:])
+    dev = cuda_dev
+    params = [t.to(dev).requires_grad_(True) for t in (wa, ba, wv, bv)]
+    plan = avc.FusePlan(fusion=fusion, fusion_scale=0.3, audio_stride=4, video_stride=2, max_seq_len=64)
+    emb, mask, lab = avc.fused_connector(a.to(dev), v.to(dev), *params, plan, prompt_ids=prompt.to(dev),
+                                         embed_table=table.to(dev, torch.bfloat16), labels=labels.to(dev),
+                                         out_dtype=torch.bfloat16, check=True)
+    (emb.float() * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(emb[:, P:], emb_r[:, P:], "AV rows")
+    assert torch.equal(emb[:, :P].cpu(), emb_r[:, :P].to(torch.bfloat16))
+    assert torch.equal(mask.cpu(), mask_r) and torch.equal(lab.cpu(), lab_r)
+    for p, gr, n in zip(params, grads_r, ["dWa", "dba", "dWv", "dbv"]):
+        assert_close(p.grad, gr, n)
+
+
+def test_ragged_video_only_placeholders_vs_oracle(avc, cuda_dev):
+    """cfg4-style: video-only, per-sample valid lengths, placeholders at ragged offsets, real masks."""
+    g = torch.Generator().manual_seed(41)
+    B, Tv, Dv, H, V, S, PH = 4, 40, 64, 128, 60, 58, 59
+    lens = [40, 17, 1, 29]
+    v = torch.randn(B, Tv, Dv, generator=g)
+    wa, ba, wv, bv = _rand_params(g, H, 8, Dv)
+    table = torch.randn(V, H, generator=g)
+    ids = torch.zeros(B, S, dtype=torch.int64)
+    for b, n in enumerate(lens):
+        row = torch.randint(1, PH, (S,), generator=g)
+        start = 2 + 3 * b
+        row[start:start + n] = PH
+        row[start + n + 4:] = 0
+        ids[b] = row
+    spec = O.ConnectorSpec(modality="video", mask_mode=1, label_mode=1)
+    tok_r, _ = O.connector_tokens(None, v, wa, ba, wv, bv, spec, video_valid=torch.tensor(lens))
+    emb_r, mask_r, lab_r = O.splice_tokens(tok_r, ids, PH, table, 0, spec, ntok=torch.tensor(lens))
+    dev = cuda_dev
+    wv_d, bv_d = wv.to(dev).requires_grad_(True), bv.to(dev).requires_grad_(True)
+    plan = avc.FusePlan(modality="video", mask_mode=1, label_mode=1)
+    emb, mask, lab = avc.fused_connector(None, v.to(dev), None, None, wv_d, bv_d, plan, input_ids=ids.to(dev),
+                                         placeholder_id=PH, embed_table=table.to(dev, torch.bfloat16),
+                                         out_dtype=torch.bfloat16, video_lengths=lens, check=True)
+    up = torch.randn(B, S, H, generator=g)
+    (emb.float() * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    is_ph = ids == PH
+    assert_close(emb[is_ph.to(dev)], emb_r[is_ph], "AV rows")
+    assert torch.equal(emb.cpu()[~is_ph], emb_r[~is_ph].to(torch.bfloat16))
+    assert torch.equal(mask.cpu(), mask_r) and torch.equal(lab.cpu(), lab_r)
+    # oracle gradients: upstream restricted to the placeholder rows, per sample
+    wv_c, bv_c = wv.clone().requires_grad_(True), bv.clone().requires_grad_(True)
+    tok, _ = O.connector_tokens(None, v, wa, ba, wv_c, bv_c, spec, video_valid=torch.tensor(lens))
+    loss = sum((tok[b, :n] * up[b][is_ph[b]]).sum() for b, n in enumerate(lens))
+    loss.backward()
+    assert_close(wv_d.grad, wv_c.grad, "dWv")
+    assert_close(bv_d.grad, bv_c.grad, "dbv")
+
+
+def test_adaptive_projection_fwd_bwd(avc, cuda_dev):
+    """Train-time length adaptation kernels vs the oracle restatement of _adaptive_projection."""
+    g = torch.Generator().manual_seed(51)
+    for S, Lt in [(28, 10), (8, 19), (1500, 256)]:
+        x = torch.randn(2, S, 64, generator=g)
+        up = torch.randn(2, Lt, 64, generator=g)
+        xc = x.clone().requires_grad_(True)
+        ref = O.reference_adaptive_projection(xc, Lt)
+        (ref * up).sum().backward()
+        xd = x.to(cuda_dev).requires_grad_(True)
+        out = avc.adaptive_projection(xd, Lt)
+        (out * up.to(cuda_dev)).sum().backward()
+        torch.cuda.synchronize()
+        # fp32 in, fp32 accumulate: only the order of the window sum differs
+        assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(xd.grad.cpu(), xc.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_no_cpu_fallback(avc, cuda_dev):
+    plan = avc.FusePlan(modality="audio")
+    w, b = torch.zeros(16, 8), torch.zeros(16)
+    with pytest.raises(avc._lib.ConnectorError):
+        avc.fused_connector(torch.zeros(1, 4, 8), None, w, b, None, None, plan)
+    with pytest.raises(avc._lib.ConnectorError):
+        avc.ClipWhisperModel(device="cpu", _provided_llm=object(), _provided_tokenizer=object())
