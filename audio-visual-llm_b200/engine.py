@@ -1,0 +1,185 @@
+"""Static-buffer training-step engine for the connector: one `step()` = the whole hot path once,
+fwd + bwd, with every buffer pre-allocated (no allocator traffic, CUDA-graph friendly).
+
+    pack weights -> gather -> projector GEMM -> splice (+masks)          forward
+    splice-bwd -> dW GEMM -> bias column sums [-> grad all-reduce]       backward
+
+This is the same kernel sequence `connector_ops._FusedConnectorFn` runs under autograd; the engine exists so
+the data-parallel trainer (and bench.py) can drive it without per-step Python allocation.  The projector
+gradients land in ONE flat fp32 bucket ([dWa | dWv | dba | dbv]) so the only collective of the path -- the
+all-reduce the trainer needs between backward() and clip_grad_norm_ (clip_whisper_trainer.py:454-458) -- is a
+single NCCL call.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .connector_ops import FusePlan
+from .parallel import GradBucket
+
+
+@dataclass(frozen=True)
+class StepShape:
+    batch: int
+    audio_frames: int
+    video_frames: int
+    audio_dim: int
+    video_dim: int
+    hidden: int
+    prompt_len: int = 16
+    vocab: int = 32000
+    label_len: int = 256
+
+
+class ConnectorStep:
+    def __init__(self, shape: StepShape, plan: FusePlan, device, out_dtype=torch.bfloat16, seed: int = 0,
+                 process_group=None):
+        if out_dtype != torch.bfloat16:
+            raise L.ConnectorError("the step engine runs the bf16 training configuration")
+        L.require_device(torch.device(device).index or 0)
+        self.shape, self.plan, self.device = shape, plan, torch.device(device)
+        s, p, dev = shape, plan, self.device
+        self.use_a = p.modality in ("audio", "both")
+        self.use_v = p.modality in ("video", "both")
+        self.sa, self.sv = p.scales(self.use_a, self.use_v)
+        self.N = p.tokens(s.audio_frames if self.use_a else None, s.video_frames if self.use_v else None)
+        self.M = s.batch * self.N
+        self.Ka = p.audio_stride * s.audio_dim if self.use_a else 0
+        self.Kv = p.video_stride * s.video_dim if self.use_v else 0
+        self.K = self.Ka + self.Kv
+        self.S = s.prompt_len + self.N
+        self.placeholder_id = s.vocab  # one past the text vocabulary
+        H = s.hidden
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        bf = torch.bfloat16
+
+        def randn(*shape_, scale=1.0):
+            return (torch.randn(*shape_, generator=g) * scale)
+
+        # ---- parameters (fp32 masters, reference init scale) and the flat gradient bucket
+        self.wa = randn(H, self.Ka, scale=(6.0 / (H + self.Ka)) ** 0.5).to(dev) if self.use_a else None
+        self.wv = randn(H, self.Kv, scale=(6.0 / (H + self.Kv)) ** 0.5).to(dev) if self.use_v else None
+        self.ba = randn(H, scale=0.02).to(dev) if self.use_a else None
+        self.bv = randn(H, scale=0.02).to(dev) if self.use_v else None
+        sizes: Dict[str, tuple] = {}
+        if self.use_a:
+            sizes["audio_connector.linear.weight"] = (H, self.Ka)
+        if self.use_v:
+            sizes["video_connector.linear.weight"] = (H, self.Kv)
+        if self.use_a:
+            sizes["audio_connector.linear.bias"] = (H,)
+        if self.use_v:
+            sizes["video_connector.linear.bias"] = (H,)
+        self.bucket = GradBucket(sizes, dev, process_group=process_group)
+        # ---- inputs resident in HBM
+        self.audio = randn(s.batch, s.audio_frames, s.audio_dim).to(bf).to(dev) if self.use_a else None
+        self.video = randn(s.batch, s.video_frames, s.video_dim).to(bf).to(dev) if self.use_v else None
+        prompt = torch.randint(1, s.vocab, (s.batch, s.prompt_len), generator=g)
+        ph = torch.full((s.batch, self.N), self.placeholder_id, dtype=torch.int64)
+        self.input_ids = torch.cat([prompt, ph], 1).to(dev)
+        labels = torch.randint(1, s.vocab, (s.batch, s.label_len), generator=g)
+        labels[:, s.label_len * 3 // 4:] = 0  # pad tail (pad id 0)
+        self.labels_in = labels.to(dev)
+        self.embed_table = randn(s.vocab + 1, H, scale=0.02).to(bf).to(dev)
+        self.d_emb = randn(s.batch, self.S, H).to(bf).to(dev)  # upstream gradient from the LLM
+        # ---- workspaces
+        self.A = torch.empty(self.M, self.K, dtype=bf, device=dev)
+        self.flags = torch.empty(self.M, dtype=torch.uint8, device=dev)
+        self.wp = torch.empty(H, self.K, dtype=bf, device=dev)
+        self.Y = torch.empty(self.M, H, dtype=bf, device=dev)
+        self.emb = torch.empty(s.batch, self.S, H, dtype=bf, device=dev)
+        self.mask = torch.empty(s.batch, self.S, dtype=torch.int64, device=dev)
+        self.labels_out = torch.empty(s.batch, self.S, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dY = torch.empty(self.M, H, dtype=bf, device=dev)
+        self.colsum_ws = L.colsum_workspace(H, dev)
+        self.sp = L.make_splice(self.input_ids, self.placeholder_id, 0, H, tokens_per_sample=self.N,
+                                embed_table=self.embed_table, attention_mask=self.mask, mask_mode=p.mask_mode,
+                                label_mode=p.label_mode, labels_in=self.labels_in, labels_out=self.labels_out,
+                                status=self.status)
+        self.launches_per_step = (int(self.use_a) + int(self.use_v)) + 1 + 1 + 1 + 1 + 1 + 2
+        self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
+
+    # ------------------------------------------------------------------ algorithmic work per step
+    @property
+    def fused_tokens(self) -> int:
+        return self.M
+
+    def gemm_flops(self) -> int:
+        return 2 * self.M * self.K * self.shape.hidden  # per GEMM launch (fwd, and again for dW)
+
+    def gather_bytes(self) -> int:
+        return 2 * self.M * self.K * 2
+
+    def splice_bytes(self) -> int:
+        return 2 * self.M * self.shape.hidden * 2 + 16 * self.shape.batch * self.S
+
+    # ------------------------------------------------------------------ the step
+    def enable_kernel_timing(self, names=("gather", "proj_fwd", "splice_fwd", "splice_bwd", "proj_bwd_dw", "colsum")):
+        self.events = {n: [] for n in names}
+
+    def _timed(self, name, fn):
+        if self.events is None or name not in self.events:
+            fn()
+            return
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        self.events[name].append((s, e))
+
+    def forward(self):
+        p = self.plan
+        col = 0
+        if self.use_a:
+            L.pack_weight(self.wa, self.wp[:, :self.Ka], self.sa)
+            col = self.Ka
+        if self.use_v:
+            L.pack_weight(self.wv, self.wp[:, col:], self.sv)
+        self._timed("gather", lambda: L.gather_fwd(self.audio, self.video, p.audio_stride, p.video_stride,
+                                                   self.shape.batch, self.N, self.A, self.flags))
+        if self.use_a and self.use_v:
+            b0, b1, s0, s1 = self.ba, self.bv, self.sa, self.sv
+        elif self.use_a:
+            b0, b1, s0, s1 = self.ba, None, self.sa, 0.0
+        else:
+            b0, b1, s0, s1 = None, self.bv, 0.0, self.sv
+        self._timed("proj_fwd", lambda: L.proj_fwd([self.A], [self.wp], self.Y, bias0=b0, bias1=b1, bias_scale0=s0,
+                                                   bias_scale1=s1, row_flags=self.flags))
+        self._timed("splice_fwd", lambda: L.splice_fwd(self.sp, self.Y, self.emb))
+        return self.emb, self.mask, self.labels_out
+
+    def backward(self, allreduce: bool = True):
+        g = self.bucket
+        self._timed("splice_bwd", lambda: L.splice_bwd(self.sp, self.d_emb, self.dY))
+        xs, dws, al = [], [], []
+        if self.use_a:
+            xs.append(self.A[:, :self.Ka]); dws.append(g["audio_connector.linear.weight"]); al.append(self.sa)
+        if self.use_v:
+            xs.append(self.A[:, self.Ka:]); dws.append(g["video_connector.linear.weight"]); al.append(self.sv)
+        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(self.dY, xs, dws, al))
+        self._timed("colsum", lambda: L.colsum(
+            self.dY, g["audio_connector.linear.bias"] if self.use_a else None,
+            g["video_connector.linear.bias"] if self.use_v else None, self.colsum_ws, row_flags=self.flags,
+            alpha0=self.sa, alpha1=self.sv))
+        if allreduce:
+            g.allreduce()
+        return g
+
+    def step(self, allreduce: bool = True):
+        self.forward()
+        return self.backward(allreduce)
+
+    def load_inputs_from_host(self, audio_h: Optional[torch.Tensor], video_h: Optional[torch.Tensor],
+                              ids_h: torch.Tensor, labels_h: torch.Tensor):
+        """H2D copies of one step's inputs (pinned host tensors) into the resident buffers, on the current stream."""
+        if self.use_a:
+            self.audio.copy_(audio_h, non_blocking=True)
+        if self.use_v:
+            self.video.copy_(video_h, non_blocking=True)
+        self.input_ids.copy_(ids_h, non_blocking=True)
+        self.labels_in.copy_(labels_h, non_blocking=True)

@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Connector fwd+bwd benchmark (BASELINE.json metric: fused tokens/sec).
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (sm_100a kernels)
+    python bench.py --impl reference [...]                     reference arm: the oracle port on host CPU cores
+
+Workload at every N: BASELINE.json configs[1] per GPU (weak scaling) --
+Whisper-medium(1024) + CLIP ViT-L/14(1024) -> 4096, concat fusion, stride 4 (k_a=4 audio + k_v=2 video frames
+per token, rate-aligned), batch 32, 30 s clips, bf16.  One step = gather -> projector GEMM -> splice(+masks) ->
+splice-bwd -> dW GEMM -> bias sums [-> projector-grad all-reduce when N > 1]; synthetic N(0,1) features and
+random-init weights (no datasets / checkpoints offline).
+
+Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` runs the public API
+(`fused_connector` + backward) from pinned HOST tensors with the H2D copy of the step's inputs and a D2H read of
+its results inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(
+    workload="cfg2: Whisper-medium(1024)+CLIP ViT-L/14(1024)->4096, concat, stride 4 (k_a=4,k_v=2), batch 32/GPU, 30 s, bf16",
+    modality="both", fusion="concat", fusion_scale=0.5, max_seq_len=1536, audio_stride=4, video_stride=2,
+    audio_frames=1500, video_frames=750, audio_dim=1024, video_dim=1024, hidden=4096, prompt_len=16, batch_per_gpu=32,
+)
+METRIC = "connector fused tokens/sec fwd+bwd"
+UNIT = "fused tokens/s"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args, rank: int):
+    """The reference's CPU connector (oracle port) on the host cores; each step is a bounded sample of cfg2."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+
+    sample_batch = 4
+    tok_s, dt, threads = cpu_baseline.time_cpu(WORKLOAD, sample_batch, args.steps, args.warmup)
+    sample = (f"batch {sample_batch} of {WORKLOAD['batch_per_gpu']} (same shapes) per step, fp32 torch CPU, "
+              f"{args.warmup} warm-up + {args.steps} timed fwd+bwd steps")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {k: v for k, v in WORKLOAD.items()},
+        "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    entry.build()
+    import audio_visual_llm_b200 as pkg
+    from audio_visual_llm_b200.engine import ConnectorStep, StepShape
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    w = WORKLOAD
+    plan = pkg.FusePlan(modality=w["modality"], fusion=w["fusion"], fusion_scale=w["fusion_scale"],
+                        max_seq_len=w["max_seq_len"], audio_stride=w["audio_stride"], video_stride=w["video_stride"])
+    shape = StepShape(batch=w["batch_per_gpu"], audio_frames=w["audio_frames"], video_frames=w["video_frames"],
+                      audio_dim=w["audio_dim"], video_dim=w["video_dim"], hidden=w["hidden"],
+                      prompt_len=w["prompt_len"])
+    eng = ConnectorStep(shape, plan, dev, seed=1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        eng.step()
+    barrier()
+    eng.enable_kernel_timing()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        eng.step()
+    t_end.record()
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    if rank == 0:
+        time.sleep(0.15)
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = {n: sum(s.elapsed_time(e) for s, e in ev) / max(len(ev), 1) for n, ev in eng.events.items()}
+    eng.events = None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = eng.fused_tokens * world / (ms_per_step * 1e-3)
+    assert int(eng.status.item()) == 0, "placeholder / token count mismatch"
+
+    # ------------------------------------------------------------------ end to end from pinned host tensors
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, dist, pkg, eng, plan, dev, args, world)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    gemm_ms = 0.5 * (kernel_ms["proj_fwd"] + kernel_ms["proj_bwd_dw"])
+    achieved_tf = eng.gemm_flops() / (gemm_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = ROOT / "profiles" / "r01_gemm_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "proj_gemm (tcgen05 projector GEMM: fwd TN + dW NT launches, averaged)",
+                "achieved": achieved_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["tf_burst"], "traffic": traffic,
+                "peak_source": peaks["source"] + ", burst figure (step is ~1 ms, run is < 0.1 s)",
+                "flops_per_launch": eng.gemm_flops(), "avg_launch_ms": gemm_ms}
+    kernels = {
+        "gather": {"ms": kernel_ms["gather"], "GBps": eng.gather_bytes() / kernel_ms["gather"] / 1e6,
+                   "frac_hbm": eng.gather_bytes() / kernel_ms["gather"] / 1e6 / peaks["hbm"]},
+        "proj_fwd": {"ms": kernel_ms["proj_fwd"], "TFLOPs": eng.gemm_flops() / kernel_ms["proj_fwd"] / 1e9,
+                     "frac_bf16": eng.gemm_flops() / kernel_ms["proj_fwd"] / 1e9 / peaks["tf_burst"]},
+        "splice_fwd": {"ms": kernel_ms["splice_fwd"], "GBps": eng.splice_bytes() / kernel_ms["splice_fwd"] / 1e6,
+                       "frac_hbm": eng.splice_bytes() / kernel_ms["splice_fwd"] / 1e6 / peaks["hbm"]},
+        "splice_bwd": {"ms": kernel_ms["splice_bwd"], "GBps": 4 * eng.M * shape.hidden / kernel_ms["splice_bwd"] / 1e6,
+                       "frac_hbm": 4 * eng.M * shape.hidden / kernel_ms["splice_bwd"] / 1e6 / peaks["hbm"]},
+        "proj_bwd_dw": {"ms": kernel_ms["proj_bwd_dw"], "TFLOPs": eng.gemm_flops() / kernel_ms["proj_bwd_dw"] / 1e9,
+                        "frac_bf16": eng.gemm_flops() / kernel_ms["proj_bwd_dw"] / 1e9 / peaks["tf_burst"]},
+        "colsum": {"ms": kernel_ms["colsum"]},
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+
+        sb, ss, sw = 8, 3, 1
+        tok_s, dt, threads = cpu_baseline.time_cpu(WORKLOAD, sb, ss, sw)
+        cpu = {"value": tok_s, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"batch {sb} of {w['batch_per_gpu']} (same shapes), {sw} warm-up + {ss} timed fwd+bwd steps, "
+                         f"fp32 torch CPU oracle port ({dt:.2f} s/step)"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {**{k: v for k, v in WORKLOAD.items()},
+                   "global_batch": w["batch_per_gpu"] * world, "fused_tokens_per_step": eng.fused_tokens * world,
+                   "parallelism": f"dp{world}", "collective": "projector-grad all-reduce (NCCL avg, 100.7 MB fp32)" if world > 1 else "none",
+                   "l2": "no flush: one step streams ~0.9 GB (features, A, W, Y, embeds, grads) >> 126 MB L2"},
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": eng.launches_per_step * args.steps,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
+    """Public-API step from pinned host inputs: H2D(features, ids, labels) -> fused_connector fwd -> backward ->
+    D2H(masks, labels, bias grads).  Same metric, max over ranks."""
+    s = eng.shape
+    audio_h = eng.audio.cpu().pin_memory()
+    video_h = eng.video.cpu().pin_memory()
+    ids_h = eng.input_ids.cpu().pin_memory()
+    labels_h = eng.labels_in.cpu().pin_memory()
+    wa, ba, wv, bv = (t.clone().requires_grad_(True) for t in (eng.wa, eng.ba, eng.wv, eng.bv))
+    mask_h = torch.empty(s.batch, eng.S, dtype=torch.int64).pin_memory()
+    lab_h = torch.empty(s.batch, eng.S, dtype=torch.int64).pin_memory()
+    db_h = torch.empty(2, s.hidden, dtype=torch.float32).pin_memory()
+    h2d = audio_h.nbytes + video_h.nbytes + ids_h.nbytes + labels_h.nbytes
+    d2h = mask_h.nbytes + lab_h.nbytes + db_h.nbytes
+
+    def step():
+        for p in (wa, ba, wv, bv):
+            p.grad = None
+        a = audio_h.to(dev, non_blocking=True)
+        v = video_h.to(dev, non_blocking=True)
+        ids = ids_h.to(dev, non_blocking=True)
+        lab_in = labels_h.to(dev, non_blocking=True)
+        emb, mask, lab = pkg.fused_connector(a, v, wa, ba, wv, bv, plan, input_ids=ids,
+                                             placeholder_id=eng.placeholder_id, embed_table=eng.embed_table,
+                                             labels=lab_in, out_dtype=torch.bfloat16)
+        emb.backward(eng.d_emb)
+        if world > 1:
+            for p in (wa, ba, wv, bv):
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        mask_h.copy_(mask, non_blocking=True)
+        lab_h.copy_(lab, non_blocking=True)
+        db_h[0].copy_(ba.grad, non_blocking=True)
+        db_h[1].copy_(bv.grad, non_blocking=True)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    return {"value": eng.fused_tokens * world / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "api": "fused_connector(...) + emb.backward(dLLM) from pinned host tensors"}
+
+
+if __name__ == "__main__":
+    main()

@@ -85,7 +85,7 @@ def build_model(pkg, dev, d, cfg, llm_dtype, Da=32, Dv=16, **kw):
         device="cuda:0", modality=cfg["modality"], max_seq_len=cfg["max_seq_len"], fusion_scale=cfg["fs"],
         _provided_tokenizer=SimpleNamespace(pad_token_id=0), _provided_llm=StubLLM(table).to(dev),
         _provided_whisper=StubWhisper(Da).to(dev), _provided_clip=StubClip(Dv).to(dev), **kw)
-    sd = {k[len("in."):]: v.to(dev) for k, v in d.items() if "connector.linear" in k}
+    sd = {k[len("in."):]: v.to(dev) for k, v in d.items() if k.startswith("in.") and "connector.linear" in k}
     missing = m.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys
     return m
