@@ -1,0 +1,65 @@
+"""CPU: the C-ABI shared library builds, loads without a GPU, and exports exactly what include/*.h declares."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "avconnector_b200.h"
+
+
+def declared_symbols():
+    text = HEADER.read_text()
+    return sorted(set(re.findall(r"AVC_API\s+[\w\s\*]+?\b(avc_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_path_entry_points():
+    syms = declared_symbols()
+    for need in ("avc_gather_fwd", "avc_proj_fwd", "avc_proj_bwd_dw", "avc_colsum", "avc_splice_fwd",
+                 "avc_splice_bwd", "avc_pack_weight", "avc_row_resample", "avc_device_check", "avc_last_error"):
+        assert need in syms
+
+
+def test_library_exports_every_declared_symbol(avc):
+    lib = ctypes.CDLL(str(avc._lib.lib_path()))
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in {HEADER.name} but not exported"
+    assert sorted(avc._lib.EXPORTS) == declared_symbols()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(avc._lib.lib_path())], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (avc_\w+)", out)))
+    assert exported == declared_symbols(), "library exports symbols the header does not declare (or vice versa)"
+
+
+def test_library_is_sm100a_native_code(avc):
+    """tcgen05 / TMA must be in the SASS (UTC*MMA, LDTM, UTMALDG/UTMASTG, UBLKCP), and no legacy HMMA."""
+    r = subprocess.run(["cuobjdump", "-sass", str(avc._lib.lib_path())], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = r.stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_no_gpu_means_loud_failure_not_fallback(avc):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = avc._lib
+    assert L.load().avc_abi_version() == L.AVC_ABI_VERSION
+    with pytest.raises(L.ConnectorError):
+        L.require_device(0)
+    with pytest.raises(L.ConnectorError):
+        avc.fused_connector(torch.zeros(1, 4, 8), None, torch.zeros(16, 8), torch.zeros(16), None, None,
+                            avc.FusePlan(modality="audio"))
+    with pytest.raises(L.ConnectorError):
+        avc.ModalityConnector(8, 16, device="cpu")(torch.zeros(1, 2, 8))
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "audio-visual-llm_b200").rglob("*.py"):
+        assert "oracle" not in p.read_text().replace("oracle/", ""), f"{p} references the oracle"
