@@ -189,6 +189,10 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   avc::GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.nseg = nseg;
+  const int cg = avc::gemm_cta_group();
+  g.m_tiles_per_batch = static_cast<int>(ceil_div(y->rows, avc::GEMM_BM * cg));
+  g.num_m_blocks = static_cast<int>(y->batches) * g.m_tiles_per_batch;
+  g.bn = avc::pick_gemm_bn(g.num_m_blocks, &N, 1, di.num_sms / cg);
   for (int s = 0; s < nseg; ++s) {
     if (a[s].cols != w[s].cols)
       return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: A has K=%lld but W has K=%lld", s,
@@ -200,16 +204,14 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
                             a[s].batch_stride, avc::GEMM_BK, avc::GEMM_BM, "proj_fwd A"))
       return rc;
     if (int rc = make_map3d(&g.mb[s], w[s].ptr, false, w[s].cols, w[s].rows, 1, w[s].row_stride, 0,
-                            avc::GEMM_BK, avc::GEMM_BN, "proj_fwd W"))
+                            avc::GEMM_BK, g.bn / cg, "proj_fwd W"))
       return rc;
     g.seg_kblocks[s] = static_cast<int>(ceil_div(a[s].cols, avc::GEMM_BK));
   }
   if (int rc = make_map3d(&g.md[0], y->ptr, y_is_fp32 != 0, N, y->rows, y->batches, y->row_stride,
                           y->batch_stride, y_is_fp32 ? 32 : 64, 32, "proj_fwd Y"))
     return rc;
-  g.m_tiles_per_batch = static_cast<int>(ceil_div(y->rows, avc::GEMM_BM));
-  g.num_m_blocks = static_cast<int>(y->batches) * g.m_tiles_per_batch;
-  g.num_n_blocks = static_cast<int>(ceil_div(N, avc::GEMM_BN));
+  g.num_n_blocks = static_cast<int>(ceil_div(N, g.bn));
   g.d_rows = static_cast<int>(y->rows);
   g.d_cols[0] = static_cast<int>(N);
   g.d_cols[1] = static_cast<int>(N);
@@ -224,7 +226,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   g.act = act;
   if ((bias0 && (reinterpret_cast<uintptr_t>(bias0) & 15)) || (bias1 && (reinterpret_cast<uintptr_t>(bias1) & 15)))
     return fail(AVC_ERR_INVALID, "proj_fwd: bias pointers must be 16-byte aligned");
-  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, y_is_fp32 != 0, di.num_sms, static_cast<cudaStream_t>(stream));
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, y_is_fp32 != 0, cg, di.num_sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_fwd launch");
   return AVC_OK;
 }
@@ -246,6 +248,11 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
     return rc;
   int64_t red_rows = 0;
   int n_blocks[2] = {0, 0};
+  int64_t n_ext[2] = {0, 0};
+  for (int s = 0; s < nseg; ++s) n_ext[s] = x[s].cols;
+  const int cg = avc::gemm_cta_group();
+  g.num_m_blocks = static_cast<int>(ceil_div(H, avc::GEMM_BM * cg));
+  g.bn = avc::pick_gemm_bn(g.num_m_blocks, n_ext, nseg, di.num_sms / cg);
   for (int s = 0; s < nseg; ++s) {
     if (x[s].batches != dy->batches) return fail(AVC_ERR_INVALID, "proj_bwd_dw: segment %d: batch mismatch", s);
     if (x[s].cols % 8 != 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: K must be a multiple of 8");
@@ -258,18 +265,17 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
                             "proj_bwd_dw dW"))
       return rc;
     red_rows = x[s].rows > red_rows ? x[s].rows : red_rows;
-    n_blocks[s] = static_cast<int>(ceil_div(x[s].cols, avc::GEMM_BN));
+    n_blocks[s] = static_cast<int>(ceil_div(x[s].cols, g.bn));
     g.d_cols[s] = static_cast<int>(x[s].cols);
     g.alpha[s] = alpha != nullptr ? alpha[s] : 1.f;
   }
-  g.num_m_blocks = static_cast<int>(ceil_div(H, avc::GEMM_BM));
   g.num_n_blocks = n_blocks[0] + n_blocks[1];
   g.n_blocks_seg0 = n_blocks[0];
   g.red_batches = static_cast<int>(dy->batches);
   g.red_kblocks_per_batch = static_cast<int>(ceil_div(red_rows, avc::GEMM_BK));
   g.a_row_base = dy_row_base;
   g.d_rows = static_cast<int>(H);
-  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, di.num_sms, static_cast<cudaStream_t>(stream));
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, cg, di.num_sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_bwd_dw launch");
   return AVC_OK;
 }

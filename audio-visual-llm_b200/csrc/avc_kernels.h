@@ -22,6 +22,7 @@ struct GemmArgs {
   CUtensorMap md[2];  // TN: md[0] = output.                 NT: output per segment
   int num_m_blocks;
   int num_n_blocks;
+  int bn;  // N tile of this launch: 64 | 128 | 192 | 256 (B tensor-map box rows / atoms must match)
   // TN
   int m_tiles_per_batch;  // an M tile never straddles two batch entries
   int nseg;               // K segments
@@ -46,7 +47,12 @@ struct GemmArgs {
 };
 
 size_t gemm_smem_bytes();
-cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int max_ctas,
+// N tile that minimises (waves x per-tile time) for `m_blocks` x ceil(n_s / bn) tiles on `num_sms` persistent CTAs.
+int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_workers);
+// 2 (default): CTA pairs with tcgen05.mma.cta_group::2 (256-row tiles); 1: single-CTA tiles (AVC_GEMM_CTA_GROUP)
+int gemm_cta_group();
+// num_m_blocks counts blocks of cta_group * GEMM_BM rows; the B tensor-map box must hold bn / cta_group rows (TN)
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int num_sms,
                         cudaStream_t stream);
 
 // ------------------------------------------------------------------ gather (align + stack + concat)

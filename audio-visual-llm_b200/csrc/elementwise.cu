@@ -54,20 +54,33 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(const __grid
   const int col = (blockIdx.y * CS_THREADS + threadIdx.x) * 8;
   if (col >= a.cols) return;
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t g = g0; g < g1; ++g) {
-    const int b = static_cast<int>(g / a.rows);
-    const int r = static_cast<int>(g - static_cast<int64_t>(b) * a.rows);
-    bool f0, f1;
-    if (a.row_flags != nullptr) {
-      const uint8_t fl = __ldg(a.row_flags + g);
-      f0 = fl & 1; f1 = fl & 2;
-    } else {
-      f0 = r < a.flag_rows0; f1 = r < a.flag_rows1;
+  constexpr int U = 8;  // independent 16-byte loads in flight per thread
+  for (int64_t gb = g0; gb < g1; gb += U) {
+    int4 v[U];
+    bool f0[U], f1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = gb + u;
+      f0[u] = f1[u] = false;
+      v[u] = make_int4(0, 0, 0, 0);
+      if (g < g1) {
+        const int b = static_cast<int>(g / a.rows);
+        const int r = static_cast<int>(g - static_cast<int64_t>(b) * a.rows);
+        if (a.row_flags != nullptr) {
+          const uint8_t fl = __ldg(a.row_flags + g);
+          f0[u] = fl & 1; f1[u] = fl & 2;
+        } else {
+          f0[u] = r < a.flag_rows0; f1[u] = r < a.flag_rows1;
+        }
+        if (f0[u] || f1[u])
+          v[u] = ld_nc_v4(a.dy + b * a.batch_stride + r * a.row_stride + static_cast<int64_t>(col) * 2);
+      }
     }
-    if (!(f0 || f1)) continue;
-    const int4 v = ld_nc_v4(a.dy + b * a.batch_stride + r * a.row_stride + static_cast<int64_t>(col) * 2);
-    if (f0) acc_bf16x8(s0, v);
-    if (f1) acc_bf16x8(s1, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // fixed order: deterministic
+      if (f0[u]) acc_bf16x8(s0, v[u]);
+      if (f1[u]) acc_bf16x8(s1, v[u]);
+    }
   }
   float* p0 = a.workspace + (static_cast<int64_t>(blockIdx.x) * 2 + 0) * a.cols + col;
   float* p1 = a.workspace + (static_cast<int64_t>(blockIdx.x) * 2 + 1) * a.cols + col;
@@ -77,17 +90,41 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(const __grid
   *reinterpret_cast<float4*>(p1 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
 }
 
+// out[col] = alpha * sum over chunks, in a fixed order: 32 columns x 8 slices per CTA; slice s adds chunks
+// s, s+8, ... (independent loads in flight), then the 8 slice sums are added in order 0..7.
 __global__ void __launch_bounds__(CS_THREADS) colsum_final_kernel(const __grid_constant__ ColsumArgs a,
                                                                   int nchunks) {
-  const int col = blockIdx.x * CS_THREADS + threadIdx.x;
-  if (col >= a.cols) return;
+  __shared__ float red[2][8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
   float s0 = 0.f, s1 = 0.f;
-  for (int c = 0; c < nchunks; ++c) {  // fixed order: deterministic
-    s0 += a.workspace[(static_cast<int64_t>(c) * 2 + 0) * a.cols + col];
-    s1 += a.workspace[(static_cast<int64_t>(c) * 2 + 1) * a.cols + col];
+  if (col < a.cols) {
+    int c = slice;
+    for (; c + 24 < nchunks; c += 32) {
+      float x0[4], x1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        x0[u] = a.workspace[(static_cast<int64_t>(c + 8 * u) * 2 + 0) * a.cols + col];
+        x1[u] = a.workspace[(static_cast<int64_t>(c + 8 * u) * 2 + 1) * a.cols + col];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s0 += x0[u]; s1 += x1[u]; }
+    }
+    for (; c < nchunks; c += 8) {
+      s0 += a.workspace[(static_cast<int64_t>(c) * 2 + 0) * a.cols + col];
+      s1 += a.workspace[(static_cast<int64_t>(c) * 2 + 1) * a.cols + col];
+    }
   }
-  if (a.out0 != nullptr) a.out0[col] = a.alpha0 * s0;
-  if (a.out1 != nullptr) a.out1[col] = a.alpha1 * s1;
+  red[0][slice][lane] = s0;
+  red[1][slice][lane] = s1;
+  __syncthreads();
+  if (slice == 0 && col < a.cols) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { t0 += red[0][s][lane]; t1 += red[1][s][lane]; }
+    if (a.out0 != nullptr) a.out0[col] = a.alpha0 * t0;
+    if (a.out1 != nullptr) a.out1[col] = a.alpha1 * t1;
+  }
 }
 
 // out[b, i, :] = sum_{t in [row_ptr[i], row_ptr[i+1])} weight[t] * x[b, col[t], :]   (fp32 accumulate)
@@ -177,7 +214,7 @@ cudaError_t launch_colsum(const ColsumArgs& a, cudaStream_t stream) {
   colsum_partial_kernel<<<grid, CS_THREADS, 0, stream>>>(a, rows_per_chunk > 0 ? rows_per_chunk : 1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  colsum_final_kernel<<<(a.cols + CS_THREADS - 1) / CS_THREADS, CS_THREADS, 0, stream>>>(a, nchunks);
+  colsum_final_kernel<<<(a.cols + 31) / 32, CS_THREADS, 0, stream>>>(a, nchunks);
   return cudaGetLastError();
 }
 

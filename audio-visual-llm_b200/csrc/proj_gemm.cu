@@ -6,11 +6,19 @@
 // This replaces the two nn.Linear calls + pad + weighted sum of the reference
 // (modality_connector.py:43-44, clip_whisper_model.py:424-434) and their autograd dW.
 //
-// Structure: persistent CTAs (one per SM), 6 warps:
-//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages of 48 KB)
+// Structure: persistent CTAs, 6 warps:
+//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      tcgen05.mma issuer (one thread), owns the TMEM allocation (512 columns = 2 accumulators)
 //   warps 2..5  epilogue: tcgen05.ld (TMEM -> registers) -> bias/GELU/scale -> swizzled smem -> TMA store
 // The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// CG = 1: one CTA per SM computes a 128 x bn tile (4 stages of 16 KB A + 32 KB B).
+// CG = 2: a CTA pair (cluster of 2, one TPC) computes a 256 x bn tile with tcgen05.mma.cta_group::2:
+//         each CTA stages its own 128 rows of A and HALF of B (6 stages of 16 KB + 16 KB), the leader CTA
+//         issues the MMAs for both, each CTA's TMEM receives its 128 rows, each CTA runs its own epilogue.
+//         Shared-memory traffic per FLOP drops by a third, which is what bounds the single-CTA kernel.
+#include <cstdlib>
+
 #include "avc_kernels.h"
 #include "avc_ptx.cuh"
 
@@ -20,30 +28,39 @@ namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 4;
-constexpr int EPI_BUF_BYTES = 32 * 128;                       // 32 rows x 128 B per warp per buffer
-constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;      // 32 KB
+constexpr int EPI_BUF_BYTES = 32 * 128;                   // 32 rows x 128 B per warp per buffer
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KB
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_USED = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-constexpr int SMEM_ALLOC = SMEM_USED + 1024;  // slack for manual 1024-B alignment
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
 constexpr int MN_ATOM_BYTES = BK * 128;  // one 64-wide MN-major atom column: BK rows x 128 B
+constexpr int kMaxStages = 6;
 
-static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of dynamic shared memory");
+template <int CG>
+struct Cfg {
+  static constexpr int kStages = CG == 2 ? 6 : 4;
+  static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;  // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM_USED = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int SMEM_ALLOC = SMEM_USED + 1024;  // slack for manual 1024-B alignment
+  static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of dynamic shared memory");
+  static_assert(kStages <= kMaxStages, "barrier area too small");
+};
 static_assert(kAccStages * BN <= kTmemCols, "accumulators exceed TMEM");
+static_assert((2 * kMaxStages + 2 * kAccStages) * 8 + 8 <= BAR_BYTES, "barrier area too small");
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int MODE, bool OUT_F32>
+template <int MODE, bool OUT_F32, int CG>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
+  using C = Cfg<CG>;
+  constexpr int kStages = C::kStages;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_epi = smem_base + kStages * STAGE_BYTES;
@@ -56,6 +73,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // position inside the CTA pair
+  const bool leader = rank == 0;
+  const int worker = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.ma[0]);
@@ -70,21 +91,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
       for (int a = 0; a < kAccStages; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), EPI_WARPS);
+        mbar_init(tempty_bar(a), EPI_WARPS * CG);  // epilogue warps of every CTA of the group
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(s_tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(s_tmem_slot, kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(s_tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_slot));
 
-  const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+  const int num_tiles = args.num_m_blocks * args.num_n_blocks;  // m blocks of CG*128 rows
+  const int bn = args.bn;        // runtime N tile (multiple of 64, <= BN)
+  const int bn_cta = bn / CG;    // B rows / columns this CTA stages
+  const int nb_boxes = (bn_cta + 63) / 64;  // NT: 64-wide MN atoms this CTA loads for B
+  // bytes this CTA's TMA loads deliver per stage (OOB parts of a box are zero-filled and still counted)
+  const uint32_t cta_tx = A_STAGE_BYTES + (MODE == GEMM_TN ? static_cast<uint32_t>(bn_cta) * (BK * 2)
+                                                            : static_cast<uint32_t>(nb_boxes) * MN_ATOM_BYTES);
   const int total_kb = (MODE == GEMM_TN)
                            ? (args.seg_kblocks[0] + (args.nseg > 1 ? args.seg_kblocks[1] : 0))
                            : (args.red_batches * args.red_kblocks_per_batch);
@@ -93,41 +126,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // ======================================================================= TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+        if (CG == 2) tma_load_3d_cg2(dst, m, bar & kPeerBitMask, c0, c1, c2);
+        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      };
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int m_blk = tile / args.num_n_blocks;
         const int n_blk = tile % args.num_n_blocks;
         if (MODE == GEMM_TN) {
           const int b = m_blk / args.m_tiles_per_batch;
-          const int r0 = (m_blk % args.m_tiles_per_batch) * BM;
-          const int n0 = n_blk * BN;
+          const int r0 = (m_blk % args.m_tiles_per_batch) * (BM * CG) + static_cast<int>(rank) * BM;
+          const int n0 = n_blk * bn + static_cast<int>(rank) * bn_cta;
           for (int seg = 0; seg < args.nseg; ++seg) {
             for (int kb = 0; kb < args.seg_kblocks[seg]; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), cta_tx * CG);
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
-              tma_load_3d(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b);
-              tma_load_3d(sa + A_STAGE_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0);
+              load(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b);
+              load(sa + A_STAGE_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
         } else {
-          const int m0 = m_blk * BM;
+          const int m0 = m_blk * (BM * CG) + static_cast<int>(rank) * BM;
           const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
-          const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * BN;
+          const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + static_cast<int>(rank) * bn_cta;
           for (int bb = 0; bb < args.red_batches; ++bb) {
             for (int kb = 0; kb < args.red_kblocks_per_batch; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), cta_tx * CG);
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               const int row = kb * BK;
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i)
-                tma_load_3d(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64,
-                            args.a_row_base + row, bb);
-#pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_3d(sa + A_STAGE_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage),
-                            nl0 + i * 64, row, bb);
+                load(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64, args.a_row_base + row, bb);
+              for (int i = 0; i < nb_boxes; ++i)
+                load(sa + A_STAGE_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage), nl0 + i * 64, row, bb);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -136,12 +170,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ======================================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc =
-          make_idesc_bf16(BM, BN, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
+    // ======================================================================= MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_bf16(BM * CG, bn, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -165,12 +198,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               da = make_smem_desc_sw128(sa + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
               db = make_smem_desc_sw128(sb + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
             }
-            umma_f16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_cg2(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+          if (CG == 2) umma_commit_cg2(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_cg2(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -180,21 +218,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const int q = warp & 3;    // TMEM lane quarter this warp may access
     const int ew = warp - 2;   // staging buffer owner index
     constexpr int COLS = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
-    constexpr int NCHUNK = BN / COLS;
+    const int nchunk = bn / COLS;
     uint32_t acc = 0, acc_phase = 0, buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_blk = tile / args.num_n_blocks;
       const int n_blk = tile % args.num_n_blocks;
       int out_row0, out_batch, out_col0, seg = 0;
       if (MODE == GEMM_TN) {
         out_batch = m_blk / args.m_tiles_per_batch;
-        out_row0 = (m_blk % args.m_tiles_per_batch) * BM + q * 32;
-        out_col0 = n_blk * BN;
+        out_row0 = (m_blk % args.m_tiles_per_batch) * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
+        out_col0 = n_blk * bn;
       } else {
         out_batch = 0;
-        out_row0 = m_blk * BM + q * 32;
+        out_row0 = m_blk * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
         seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
-        out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * BN;
+        out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn;
       }
       const int my_row = out_row0 + lane;
       float f0 = 0.f, f1 = 0.f;
@@ -220,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = 0; c < nchunk; ++c) {
         const int col = out_col0 + c * COLS;
         // the store issued from this staging buffer two chunks ago must have finished reading it
         if (lane == 0) bulk_wait_read<1>();
@@ -289,10 +327,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
         buf ^= 1u;
       }
-      // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
+      // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) bulk_wait_all<0>();
@@ -301,31 +342,82 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still signal this CTA's barriers / read its smem until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+
+template <int CG>
+cudaError_t launch_cg(const GemmArgs& args, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
+  const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+  const int max_workers = num_sms / CG;
+  const int workers = num_tiles < max_workers ? num_tiles : max_workers;
+  auto run = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * CG);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<CG>::SMEM_ALLOC;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args);
+  };
+  if (mode == GEMM_TN)
+    return out_fp32 ? run(gemm_kernel<GEMM_TN, true, CG>) : run(gemm_kernel<GEMM_TN, false, CG>);
+  return out_fp32 ? run(gemm_kernel<GEMM_NT, true, CG>) : run(gemm_kernel<GEMM_NT, false, CG>);
 }
 
 }  // namespace
 
-size_t gemm_smem_bytes() { return SMEM_ALLOC; }
+size_t gemm_smem_bytes() { return Cfg<1>::SMEM_ALLOC; }
 
-cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int max_ctas,
+int gemm_cta_group() {
+  const int v = env_int("AVC_GEMM_CTA_GROUP", 2);
+  return v == 1 ? 1 : 2;
+}
+
+int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_workers) {
+  const int forced = env_int("AVC_GEMM_BN", 0);
+  if (forced == 64 || forced == 128 || forced == 192 || forced == 256) return forced;
+  // Persistent workers run ceil(tiles / workers) rounds; a tile's time grows with bn plus a fixed part (the
+  // A-operand shared-memory traffic, pipeline fill/drain, epilogue tail).  Measured on B200: narrower tiles
+  // lose far more to operand traffic than they win back from wave quantisation, hence the large constant.
+  int best = 256;
+  double best_cost = 1e30;
+  const int cand[2] = {256, 128};
+  for (int c = 0; c < 2; ++c) {
+    const int bn = cand[c];
+    int64_t tiles = 0;
+    for (int s = 0; s < nseg; ++s) tiles += static_cast<int64_t>(m_blocks) * ((n_extent[s] + bn - 1) / bn);
+    const int64_t rounds = (tiles + num_workers - 1) / num_workers;
+    const double cost = static_cast<double>(rounds) * (bn + 128);
+    if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int num_sms,
                         cudaStream_t stream) {
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
   if (num_tiles <= 0) return cudaSuccess;
-  const int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
-  auto run = [&](auto kern) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, kThreads, SMEM_ALLOC, stream>>>(args);
-    return cudaGetLastError();
-  };
-  if (mode == GEMM_TN) {
-    return out_fp32 ? run(gemm_kernel<GEMM_TN, true>) : run(gemm_kernel<GEMM_TN, false>);
-  }
-  return out_fp32 ? run(gemm_kernel<GEMM_NT, true>) : run(gemm_kernel<GEMM_NT, false>);
+  if (args.bn < 64 || args.bn > BN || args.bn % 64 != 0) return cudaErrorInvalidValue;
+  if (cta_group == 2) return launch_cg<2>(args, mode, out_fp32, num_sms, stream);
+  return launch_cg<1>(args, mode, out_fp32, num_sms, stream);
 }
 
 }  // namespace avc
