@@ -23,6 +23,8 @@ struct GemmArgs {
   int num_m_blocks;
   int num_n_blocks;
   int bn;  // N tile of this launch: 64 | 128 | 192 | 256 (B tensor-map box rows / atoms must match)
+  int full_tiles;  // set by launch_gemm: tiles processed whole; the remaining ones are cut into
+  int tail_split;  // `tail_split` sub-tiles of width bn / tail_split (tail of the persistent schedule)
   // TN
   int m_tiles_per_batch;  // an M tile never straddles two batch entries
   int nseg;               // K segments

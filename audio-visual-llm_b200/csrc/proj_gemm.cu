@@ -113,8 +113,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;  // m blocks of CG*128 rows
   const int bn = args.bn;        // runtime N tile (multiple of 64, <= BN)
-  const int bn_cta = bn / CG;    // B rows / columns this CTA stages
+  const int bn_cta = bn / CG;    // B rows / columns this CTA stages (TMA box); sub-tiles use a prefix of it
   const int nb_boxes = (bn_cta + 63) / 64;  // NT: 64-wide MN atoms this CTA loads for B
+  // Work list: `full_tiles` whole tiles (a multiple of the worker count), then the leftover tiles of the last,
+  // partial round cut into `tail_split` narrower sub-tiles so that the tail spreads over all workers.
+  const int full_tiles = args.full_tiles;
+  const int tail_split = args.tail_split;
+  const int total_work = full_tiles + (num_tiles - full_tiles) * tail_split;
+  auto decode = [&](int w, int& m_blk, int& n_blk, int& n_off, int& width) {
+    int tile = w;
+    n_off = 0;
+    width = bn;
+    if (w >= full_tiles) {
+      const int u = w - full_tiles;
+      tile = full_tiles + u / tail_split;
+      width = bn / tail_split;
+      n_off = (u % tail_split) * width;
+    }
+    m_blk = tile / args.num_n_blocks;
+    n_blk = tile % args.num_n_blocks;
+  };
   // bytes this CTA's TMA loads deliver per stage (OOB parts of a box are zero-filled and still counted)
   const uint32_t cta_tx = A_STAGE_BYTES + (MODE == GEMM_TN ? static_cast<uint32_t>(bn_cta) * (BK * 2)
                                                             : static_cast<uint32_t>(nb_boxes) * MN_ATOM_BYTES);
@@ -130,13 +148,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (CG == 2) tma_load_3d_cg2(dst, m, bar & kPeerBitMask, c0, c1, c2);
         else tma_load_3d(dst, m, bar, c0, c1, c2);
       };
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m_blk = tile / args.num_n_blocks;
-        const int n_blk = tile % args.num_n_blocks;
+      for (int w = worker; w < total_work; w += num_workers) {
+        int m_blk, n_blk, n_off, width;
+        decode(w, m_blk, n_blk, n_off, width);
+        const int w_cta = width / CG;  // B rows / columns of this CTA that the MMA reads
         if (MODE == GEMM_TN) {
           const int b = m_blk / args.m_tiles_per_batch;
           const int r0 = (m_blk % args.m_tiles_per_batch) * (BM * CG) + static_cast<int>(rank) * BM;
-          const int n0 = n_blk * bn + static_cast<int>(rank) * bn_cta;
+          const int n0 = n_blk * bn + n_off + static_cast<int>(rank) * w_cta;
           for (int seg = 0; seg < args.nseg; ++seg) {
             for (int kb = 0; kb < args.seg_kblocks[seg]; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         } else {
           const int m0 = m_blk * (BM * CG) + static_cast<int>(rank) * BM;
           const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
-          const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + static_cast<int>(rank) * bn_cta;
+          const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off + static_cast<int>(rank) * w_cta;
           for (int bb = 0; bb < args.red_batches; ++bb) {
             for (int kb = 0; kb < args.red_kblocks_per_batch; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -172,9 +191,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   } else if (warp == 1) {
     // ======================================================================= MMA issuer (leader CTA only)
     if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_bf16(BM * CG, bn, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int w = worker; w < total_work; w += num_workers) {
+        int m_blk, n_blk, n_off, width;
+        decode(w, m_blk, n_blk, n_off, width);
+        const uint32_t idesc = make_idesc_bf16(BM * CG, width, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -218,21 +239,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const int q = warp & 3;    // TMEM lane quarter this warp may access
     const int ew = warp - 2;   // staging buffer owner index
     constexpr int COLS = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
-    const int nchunk = bn / COLS;
     uint32_t acc = 0, acc_phase = 0, buf = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
-      const int m_blk = tile / args.num_n_blocks;
-      const int n_blk = tile % args.num_n_blocks;
+    for (int w = worker; w < total_work; w += num_workers) {
+      int m_blk, n_blk, n_off, width;
+      decode(w, m_blk, n_blk, n_off, width);
+      const int nchunk = width / COLS;
       int out_row0, out_batch, out_col0, seg = 0;
       if (MODE == GEMM_TN) {
         out_batch = m_blk / args.m_tiles_per_batch;
         out_row0 = (m_blk % args.m_tiles_per_batch) * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
-        out_col0 = n_blk * bn;
+        out_col0 = n_blk * bn + n_off;
       } else {
         out_batch = 0;
         out_row0 = m_blk * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
         seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
-        out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn;
+        out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off;
       }
       const int my_row = out_row0 + lane;
       float f0 = 0.f, f1 = 0.f;
@@ -356,10 +377,33 @@ int env_int(const char* name, int dflt) {
 }
 
 template <int CG>
-cudaError_t launch_cg(const GemmArgs& args, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
+cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
+  GemmArgs args = args_in;
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
-  const int max_workers = num_sms / CG;
+  int max_workers = num_sms / CG;
+  const int cap = env_int("AVC_GEMM_MAX_WORKERS", 0);  // test knob: exercise multi-round schedules on small shapes
+  if (cap > 0 && cap < max_workers) max_workers = cap;
   const int workers = num_tiles < max_workers ? num_tiles : max_workers;
+  // Tail of the persistent schedule: cut the leftover tiles of the last (partial) round into narrower
+  // sub-tiles when that shortens the round.  Sub-tile width >= 64 (one bf16 epilogue chunk).
+  args.full_tiles = num_tiles;
+  args.tail_split = 1;
+  const int leftover = num_tiles % workers;
+  if (leftover != 0 && env_int("AVC_GEMM_TAIL_SPLIT", 1) != 0) {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int split = 1; split <= 4; split *= 2) {
+      const int width = args.bn / split;
+      if (width < 64 || width % 64 != 0 || (width / CG) % 16 != 0) break;
+      const int rounds = (leftover * split + workers - 1) / workers;
+      const double cost = rounds * (width + 128.0);
+      if (cost < best_cost * 0.97) { best_cost = cost; best = split; }
+    }
+    if (best > 1) {
+      args.full_tiles = num_tiles - leftover;
+      args.tail_split = best;
+    }
+  }
   auto run = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_ALLOC);
     if (e != cudaSuccess) return e;

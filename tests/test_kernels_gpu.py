@@ -195,6 +195,37 @@ def test_proj_fwd_column_slices_of_gathered_matrix(avc, cuda_dev):
     assert rel_err(y1, ref) <= 2e-5
 
 
+@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("workers", ["3", "5"])
+def test_gemm_multi_round_schedule_with_tail_split(avc, cuda_dev, monkeypatch, cta_group, workers):
+    """Persistent schedule with several rounds per worker and a partial last round (cut into sub-tiles), for
+    both the single-CTA and the CTA-pair kernels, forward (TN, bf16 + fp32 out) and dW (NT)."""
+    L = avc._lib
+    monkeypatch.setenv("AVC_GEMM_CTA_GROUP", cta_group)
+    monkeypatch.setenv("AVC_GEMM_MAX_WORKERS", workers)
+    g = torch.Generator().manual_seed(77)
+    B, R, K, N = 2, 300, 136, 1000
+    a = bf16_randn(g, B, R, K)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    ref = proj_expected([a], [w], bias, None, torch.ones(B, R), None, 0)
+    for dt, tol in [(torch.float32, 2e-5), (torch.bfloat16, 6e-3)]:
+        y = torch.full((B, R, N), float("nan"), dtype=dt, device=cuda_dev)
+        L.proj_fwd([a.to(cuda_dev)], [w.to(cuda_dev)], y, bias0=bias.to(cuda_dev))
+        torch.cuda.synchronize()
+        assert torch.isfinite(y).all()
+        assert rel_err(y, ref) <= tol, rel_err(y, ref)
+    dy = bf16_randn(g, B, R, 520)
+    xs = [bf16_randn(g, B, R, 712), bf16_randn(g, B, R, 200)]
+    refs = [torch.einsum("brh,brk->hk", dy.double(), x.double()) for x in xs]
+    dws = [torch.full((520, x.shape[2]), float("nan"), dtype=torch.float32, device=cuda_dev) for x in xs]
+    L.proj_bwd_dw(dy.to(cuda_dev), [x.to(cuda_dev) for x in xs], dws, [1.0, 1.0])
+    torch.cuda.synchronize()
+    for dw, r in zip(dws, refs):
+        assert torch.isfinite(dw).all()
+        assert rel_err(dw, r) <= 2e-5, rel_err(dw, r)
+
+
 # ------------------------------------------------------------------------------------ projector bwd
 @pytest.mark.parametrize("B,R,H,Ka,Kv,base", [(1, 64, 128, 256, 0, 0), (2, 150, 320, 192, 72, 0), (2, 100, 256, 256, 128, 16),
                                               (1, 1000, 512, 520, 0, 0)])
