@@ -159,9 +159,11 @@ def colsum_workspace(cols: int, device) -> torch.Tensor:
 
 def colsum(dy: torch.Tensor, out0: Optional[torch.Tensor], out1: Optional[torch.Tensor], workspace: torch.Tensor,
            row_flags: Optional[torch.Tensor] = None, flag_rows0: int = 1 << 30, flag_rows1: int = 1 << 30,
-           alpha0: float = 1.0, alpha1: float = 1.0) -> None:
+           alpha0: float = 1.0, alpha1: float = 1.0, dy_row_base: int = 0, sum_rows: Optional[int] = None) -> None:
+    m = mat(dy)
     check(load().avc_colsum(
-        C.byref(mat(dy)), C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
+        C.byref(m), C.c_int32(dy_row_base), C.c_int32(m.rows - dy_row_base if sum_rows is None else sum_rows),
+        C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
         C.c_float(alpha0), C.c_float(alpha1), C.c_void_p(_ptr(out0)), C.c_void_p(_ptr(out1)),
         C.c_void_p(workspace.data_ptr()), stream_ptr()))
 

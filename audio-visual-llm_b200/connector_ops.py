@@ -176,12 +176,6 @@ class _FusedConnectorFn(torch.autograd.Function):
         if use_v and wv.shape[1] != Kv:
             raise ValueError(f"video connector expects input_dim {wv.shape[1]} but stacked video width is {Kv}")
         K = Ka + Kv
-        # 1. gather (align + stack + concat) into the packed A matrix
-        A = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
-        flags = torch.empty(M, dtype=torch.uint8, device=dev)
-        if M:
-            L.gather_fwd(audio, video, ka, kv, B, N, A, flags, st["tok_offset"], st["audio_valid"], st["video_valid"])
-        # 2. projector: one GEMM over [a ; v]
         ws = ([wa] if use_a else []) + ([wv] if use_v else [])
         wp = pack_projector(ws, ([sa] if use_a else []) + ([sv] if use_v else []))
         out_dtype = st["out_dtype"]
@@ -192,8 +186,26 @@ class _FusedConnectorFn(torch.autograd.Function):
             b0, b1, s0, s1 = ba, None, sa, 0.0
         else:  # video only: its "present" flag is bit 1
             b0, b1, s0, s1 = None, bv, 0.0, sv
-        if M:
-            L.proj_fwd([A], [wp], Y, bias0=b0, bias1=b1, bias_scale0=s0, bias_scale1=s1, row_flags=flags)
+        direct = st["tok_offset"] is None and _stack_is_free_view(audio, ka, N) and _stack_is_free_view(video, kv, N)
+        if direct:
+            # Dense streams whose frame counts divide by the stride: stacking k frames is a free reshape
+            # [B, T, D] -> [B*T/k, k*D], so the GEMM reads the tower outputs in place through one TMA descriptor
+            # per modality (two K segments) and the gathered operand is never materialised.
+            xs = ([audio.view(B * N, Ka)] if use_a else []) + ([video.view(B * N, Kv)] if use_v else [])
+            wsegs = ([wp[:, :Ka]] if use_a else []) + ([wp[:, Ka:]] if use_v else [])
+            A, flags = None, None
+            if M:
+                L.proj_fwd(xs, wsegs, Y, bias0=b0, bias1=b1, bias_scale0=s0, bias_scale1=s1)
+        else:
+            # 1. gather (align + stack + concat, zero padding, CLS stride) into the packed A matrix
+            A = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+            flags = torch.empty(M, dtype=torch.uint8, device=dev)
+            xs = ([A[:, :Ka]] if use_a else []) + ([A[:, Ka:]] if use_v else [])
+            if M:
+                L.gather_fwd(audio, video, ka, kv, B, N, A, flags, st["tok_offset"], st["audio_valid"],
+                             st["video_valid"])
+                # 2. projector: one GEMM over [a ; v]
+                L.proj_fwd([A], [wp], Y, bias0=b0, bias1=b1, bias_scale0=s0, bias_scale1=s1, row_flags=flags)
         # 3. splice into the LLM input-embedding sequence + masks
         ids = st["input_ids"]
         S = ids.shape[1]
@@ -207,11 +219,15 @@ class _FusedConnectorFn(torch.autograd.Function):
                            mask_mode=plan.mask_mode, label_mode=plan.label_mode, labels_in=st["labels"],
                            labels_out=labels_out, status=status, elem_size=4 if out_dtype == torch.float32 else 2)
         L.splice_fwd(sp, Y if M else None, emb)
-        ctx.save_for_backward(A, flags)
+        ctx.save_for_backward(*xs)
+        ctx.flags = flags
         ctx.sp = sp
         ctx.meta = (use_a, use_v, sa, sv, Ka, Kv, H, M, out_dtype)
+        # uniform `[prompt | AV]` layout built by fused_connector itself: backward may read d(inputs_embeds) in place
+        ctx.uniform = (B, N, S - N) if (st["uniform_layout"] and out_dtype == torch.bfloat16) else None
         st["status"] = status
         st["row_flags"] = flags
+        st["direct"] = direct
         ctx.mark_non_differentiable(mask)
         if labels_out is not None:
             ctx.mark_non_differentiable(labels_out)
@@ -220,7 +236,8 @@ class _FusedConnectorFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_emb, *unused):
-        A, flags = ctx.saved_tensors
+        xs = list(ctx.saved_tensors)
+        flags = ctx.flags
         use_a, use_v, sa, sv, Ka, Kv, H, M, out_dtype = ctx.meta
         dev = d_emb.device
         if d_emb.dtype != out_dtype or not d_emb.is_contiguous():
@@ -234,22 +251,39 @@ class _FusedConnectorFn(torch.autograd.Function):
                 if t is not None:
                     t.zero_()
             return dwa, dba, dwv, dbv, None
+        dws = ([dwa] if use_a else []) + ([dwv] if use_v else [])
+        al = ([sa] if use_a else []) + ([sv] if use_v else [])
+        ws = L.colsum_workspace(H, dev)
+        if ctx.uniform is not None:
+            # `[prompt | AV]`: the AV rows of sample b are rows P .. P+N-1 of d(inputs_embeds)[b]; the dW GEMM and
+            # the bias sums read them in place (no splice-bwd copy)
+            B, N, P = ctx.uniform
+            x3 = [x.view(B, N, x.shape[1]) for x in xs]
+            L.proj_bwd_dw(d_emb, x3, dws, al, dy_row_base=P)
+            if flags is None:
+                L.colsum(d_emb, dba, dbv, ws, alpha0=sa, alpha1=sv, dy_row_base=P, sum_rows=N)
+            else:
+                L.colsum(d_emb, dba, dbv, ws, row_flags=flags, alpha0=sa, alpha1=sv, dy_row_base=P, sum_rows=N)
+            return dwa, dba, dwv, dbv, None
         dY = torch.empty(M, H, dtype=out_dtype, device=dev)
         L.splice_bwd(ctx.sp, d_emb, dY)
         if out_dtype == torch.float32:
             dYb = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
             L.pack_weight(dY, dYb, 1.0)
             dY = dYb
-        xs, dws, al = [], [], []
-        if use_a:
-            xs.append(A[:, :Ka]); dws.append(dwa); al.append(sa)
-        if use_v:
-            xs.append(A[:, Ka:]); dws.append(dwv); al.append(sv)
         L.proj_bwd_dw(dY, xs, dws, al)
-        ws = L.colsum_workspace(H, dev)
-        # flag bit0 = audio token present, bit1 = video token present
+        # flag bit0 = audio token present, bit1 = video token present (all present when the stack was a free view)
         L.colsum(dY, dba, dbv, ws, row_flags=flags, alpha0=sa, alpha1=sv)
         return dwa, dba, dwv, dbv, None
+
+
+def _stack_is_free_view(x: Optional[torch.Tensor], k: int, ntok: int) -> bool:
+    """True if stacking k frames of [B, T, D] is the reshape [B*T/k, k*D] with exactly `ntok` tokens per sample."""
+    if x is None:
+        return True
+    B, T, D = x.shape
+    return (T % k == 0 and T // k == ntok and x.stride(2) == 1 and x.stride(1) == D and x.stride(0) == T * D
+            and x.data_ptr() % 16 == 0)
 
 
 def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor], wa, ba, wv, bv, plan: FusePlan, *,
@@ -295,6 +329,7 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
         tok_offset = torch.tensor(offs, dtype=torch.int32, device=dev)
         audio_valid = _as_int32(la, dev)
         video_valid = _as_int32(lv, dev)
+    uniform_layout = input_ids is None
     if input_ids is None:
         ph = torch.full((B, N), placeholder_id, dtype=torch.int64, device=dev)
         if ragged:
@@ -315,7 +350,8 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
         labels = labels.to(torch.int64).contiguous()
     st = dict(device=dev, audio=a, video=v, plan=plan, batch=B, ntok=N, rows=rows, tok_offset=tok_offset,
               audio_valid=audio_valid, video_valid=video_valid, out_dtype=out_dtype, input_ids=input_ids,
-              placeholder_id=placeholder_id, pad_id=pad_id, embed_table=embed_table, labels=labels)
+              placeholder_id=placeholder_id, pad_id=pad_id, embed_table=embed_table, labels=labels,
+              uniform_layout=uniform_layout)
     dummy = torch.zeros(0, device=dev)
     out = _FusedConnectorFn.apply(wa if use_a else dummy, ba if use_a else dummy, wv if use_v else dummy,
                                   bv if use_v else dummy, st)

@@ -282,8 +282,9 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
 
 size_t avc_colsum_workspace_bytes(int32_t cols) { return avc::colsum_workspace_bytes(cols); }
 
-int avc_colsum(const avc_mat* dy, const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, float alpha0,
-               float alpha1, float* out0, float* out1, void* workspace, void* stream) {
+int avc_colsum(const avc_mat* dy, int32_t dy_row_base, int32_t sum_rows, const uint8_t* row_flags, int32_t flag_rows0,
+               int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1, void* workspace,
+               void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (dy == nullptr || dy->ptr == nullptr) return fail(AVC_ERR_INVALID, "colsum: null dY");
@@ -294,7 +295,11 @@ int avc_colsum(const avc_mat* dy, const uint8_t* row_flags, int32_t flag_rows0, 
   c.row_stride = dy->row_stride * 2;
   c.batch_stride = dy->batch_stride * 2;
   c.batch = static_cast<int>(dy->batches);
-  c.rows = static_cast<int>(dy->rows);
+  if (dy_row_base < 0 || sum_rows < 0 || dy_row_base + sum_rows > dy->rows)
+    return fail(AVC_ERR_INVALID, "colsum: rows [%d, %d) outside the %lld rows of dY", dy_row_base,
+                dy_row_base + sum_rows, static_cast<long long>(dy->rows));
+  c.rows = sum_rows;
+  c.row_base = dy_row_base;
   c.cols = static_cast<int>(dy->cols);
   c.row_flags = row_flags;
   c.flag_rows0 = flag_rows0;

@@ -25,6 +25,8 @@ struct GemmArgs {
   int bn;  // N tile of this launch: 64 | 128 | 192 | 256 (B tensor-map box rows / atoms must match)
   int full_tiles;  // set by launch_gemm: tiles processed whole; the remaining ones are cut into
   int tail_split;  // `tail_split` sub-tiles of width bn / tail_split (tail of the persistent schedule)
+  int group_m;     // set by launch_gemm: M blocks per rasterisation group (L2 reuse of the B panels)
+  int l2_hints;    // set by launch_gemm: TMA L2 eviction hints on / off
   // TN
   int m_tiles_per_batch;  // an M tile never straddles two batch entries
   int nseg;               // K segments
@@ -116,7 +118,8 @@ struct ColsumArgs {
   const uint8_t* dy;         // [batch][rows][H] bf16
   int64_t row_stride;        // bytes
   int64_t batch_stride;      // bytes
-  int batch, rows, cols;     // rows per batch entry
+  int batch, rows, cols;     // rows summed per batch entry
+  int row_base;              // first of those rows inside each batch entry (e.g. the prompt length)
   const uint8_t* row_flags;  // [batch*rows] or nullptr (analytic)
   int flag_rows0, flag_rows1;
   float alpha0, alpha1;

@@ -238,12 +238,25 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // even (leader) CTA's copy of a barrier -- TMA issued with .cta_group::2 may signal it from either CTA.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 
+// L2 eviction-priority policies for TMA loads (createpolicy encodings)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
 __device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst_smem, const CUtensorMap* m, uint32_t leader_bar,
-                                                int c0, int c1, int c2) {
+                                                int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst_smem),
-      "l"(m), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst_smem),
+      "l"(m), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0,
+                                                 int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst_smem),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t dst_smem, uint32_t ncols) {

@@ -55,25 +55,27 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(const __grid
   if (col >= a.cols) return;
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   constexpr int U = 8;  // independent 16-byte loads in flight per thread
+  // (b, r) of the first row of this chunk; advanced incrementally (no per-row division)
+  int b = a.rows > 0 ? static_cast<int>(g0 / a.rows) : 0;
+  int r = static_cast<int>(g0 - static_cast<int64_t>(b) * a.rows);
+  const uint8_t* base = a.dy + static_cast<int64_t>(col) * 2;
   for (int64_t gb = g0; gb < g1; gb += U) {
     int4 v[U];
     bool f0[U], f1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t g = gb + u;
       f0[u] = f1[u] = false;
       v[u] = make_int4(0, 0, 0, 0);
-      if (g < g1) {
-        const int b = static_cast<int>(g / a.rows);
-        const int r = static_cast<int>(g - static_cast<int64_t>(b) * a.rows);
+      if (gb + u < g1) {
         if (a.row_flags != nullptr) {
-          const uint8_t fl = __ldg(a.row_flags + g);
+          const uint8_t fl = __ldg(a.row_flags + gb + u);
           f0[u] = fl & 1; f1[u] = fl & 2;
         } else {
           f0[u] = r < a.flag_rows0; f1[u] = r < a.flag_rows1;
         }
         if (f0[u] || f1[u])
-          v[u] = ld_nc_v4(a.dy + b * a.batch_stride + r * a.row_stride + static_cast<int64_t>(col) * 2);
+          v[u] = ld_nc_v4(base + b * a.batch_stride + static_cast<int64_t>(r + a.row_base) * a.row_stride);
+        if (++r == a.rows) { r = 0; ++b; }
       }
     }
 #pragma unroll

@@ -130,8 +130,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       width = bn / tail_split;
       n_off = (u % tail_split) * width;
     }
-    m_blk = tile / args.num_n_blocks;
-    n_blk = tile % args.num_n_blocks;
+    // grouped rasterisation: `group_m` M blocks share each sweep over N, so the tiles of one round touch
+    // ~group_m A panels and ~workers/group_m B panels instead of a few A panels and every B panel
+    const int gm = args.group_m;
+    const int per_group = gm * args.num_n_blocks;
+    const int g = tile / per_group;
+    const int first_m = g * gm;
+    const int rows_in_group = (args.num_m_blocks - first_m) < gm ? (args.num_m_blocks - first_m) : gm;
+    const int r = tile - g * per_group;
+    m_blk = first_m + r % rows_in_group;
+    n_blk = r / rows_in_group;
   };
   // bytes this CTA's TMA loads deliver per stage (OOB parts of a box are zero-filled and still counted)
   const uint32_t cta_tx = A_STAGE_BYTES + (MODE == GEMM_TN ? static_cast<uint32_t>(bn_cta) * (BK * 2)
@@ -144,10 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // ======================================================================= TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
-        if (CG == 2) tma_load_3d_cg2(dst, m, bar & kPeerBitMask, c0, c1, c2);
-        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t pol) {
+        if (CG == 2) tma_load_3d_cg2(dst, m, bar & kPeerBitMask, c0, c1, c2, pol);
+        else tma_load_3d_hint(dst, m, bar, c0, c1, c2, pol);
       };
+      // forward: activations stream through once per N sweep, the weights are re-read by every M block
+      const uint64_t pol_a = args.l2_hints ? (MODE == GEMM_TN ? kEvictFirst : kEvictNormal) : kEvictNormal;
+      const uint64_t pol_b = args.l2_hints ? (MODE == GEMM_TN ? kEvictLast : kEvictNormal) : kEvictNormal;
       for (int w = worker; w < total_work; w += num_workers) {
         int m_blk, n_blk, n_off, width;
         decode(w, m_blk, n_blk, n_off, width);
@@ -161,8 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               mbar_wait(empty_bar(stage), phase ^ 1u);
               if (leader) mbar_arrive_expect_tx(full_bar(stage), cta_tx * CG);
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
-              load(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b);
-              load(sa + A_STAGE_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0);
+              load(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b, pol_a);
+              load(sa + A_STAGE_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0, pol_b);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -178,9 +189,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               const int row = kb * BK;
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i)
-                load(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64, args.a_row_base + row, bb);
+                load(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64, args.a_row_base + row, bb,
+                     pol_a);
               for (int i = 0; i < nb_boxes; ++i)
-                load(sa + A_STAGE_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage), nl0 + i * 64, row, bb);
+                load(sa + A_STAGE_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage), nl0 + i * 64, row, bb,
+                     pol_b);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -388,6 +401,10 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
   // sub-tiles when that shortens the round.  Sub-tile width >= 64 (one bf16 epilogue chunk).
   args.full_tiles = num_tiles;
   args.tail_split = 1;
+  args.l2_hints = env_int("AVC_GEMM_L2_HINTS", 1);
+  args.group_m = env_int("AVC_GEMM_GROUP_M", 8);
+  if (args.group_m < 1) args.group_m = 1;
+  if (args.group_m > args.num_m_blocks) args.group_m = args.num_m_blocks;
   const int leftover = num_tiles % workers;
   if (leftover != 0 && env_int("AVC_GEMM_TAIL_SPLIT", 1) != 0) {
     int best = 1;

@@ -37,7 +37,7 @@ class StepShape:
 
 class ConnectorStep:
     def __init__(self, shape: StepShape, plan: FusePlan, device, out_dtype=torch.bfloat16, seed: int = 0,
-                 process_group=None):
+                 process_group=None, fuse_gather: bool = True):
         if out_dtype != torch.bfloat16:
             raise L.ConnectorError("the step engine runs the bf16 training configuration")
         L.require_device(torch.device(device).index or 0)
@@ -101,7 +101,16 @@ class ConnectorStep:
                                 embed_table=self.embed_table, attention_mask=self.mask, mask_mode=p.mask_mode,
                                 label_mode=p.label_mode, labels_in=self.labels_in, labels_out=self.labels_out,
                                 status=self.status)
-        self.launches_per_step = (int(self.use_a) + int(self.use_v)) + 1 + 1 + 1 + 1 + 1 + 2
+        # Gather-free ("direct") mode: when every stream is dense and its frame count divides by the stride, the
+        # stacked operand is a free reshape of the tower output, so the GEMMs read it in place (two K segments) and
+        # the backward reads d(inputs_embeds) in place (the `[prompt | AV]` layout puts the AV rows of sample b at
+        # rows P .. P+N-1).  Otherwise: gather -> GEMM, splice-bwd -> GEMM.
+        def free(frames, k):
+            return frames % k == 0 and frames // k == self.N
+        self.direct = bool(fuse_gather and (not self.use_a or free(s.audio_frames, p.audio_stride))
+                           and (not self.use_v or free(s.video_frames, p.video_stride)))
+        npack = int(self.use_a) + int(self.use_v)
+        self.launches_per_step = npack + (3 if self.direct else 5) + 2  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum x2
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
 
     # ------------------------------------------------------------------ algorithmic work per step
@@ -140,32 +149,49 @@ class ConnectorStep:
             col = self.Ka
         if self.use_v:
             L.pack_weight(self.wv, self.wp[:, col:], self.sv)
-        self._timed("gather", lambda: L.gather_fwd(self.audio, self.video, p.audio_stride, p.video_stride,
-                                                   self.shape.batch, self.N, self.A, self.flags))
+        if not self.direct:
+            self._timed("gather", lambda: L.gather_fwd(self.audio, self.video, p.audio_stride, p.video_stride,
+                                                       self.shape.batch, self.N, self.A, self.flags))
         if self.use_a and self.use_v:
             b0, b1, s0, s1 = self.ba, self.bv, self.sa, self.sv
         elif self.use_a:
             b0, b1, s0, s1 = self.ba, None, self.sa, 0.0
         else:
             b0, b1, s0, s1 = None, self.bv, 0.0, self.sv
-        self._timed("proj_fwd", lambda: L.proj_fwd([self.A], [self.wp], self.Y, bias0=b0, bias1=b1, bias_scale0=s0,
-                                                   bias_scale1=s1, row_flags=self.flags))
+        if self.direct:
+            xs = ([self.audio.view(self.M, self.Ka)] if self.use_a else []) + \
+                 ([self.video.view(self.M, self.Kv)] if self.use_v else [])
+            wsegs = ([self.wp[:, :self.Ka]] if self.use_a else []) + ([self.wp[:, self.Ka:]] if self.use_v else [])
+            self._timed("proj_fwd", lambda: L.proj_fwd(xs, wsegs, self.Y, bias0=b0, bias1=b1, bias_scale0=s0,
+                                                       bias_scale1=s1))
+        else:
+            self._timed("proj_fwd", lambda: L.proj_fwd([self.A], [self.wp], self.Y, bias0=b0, bias1=b1,
+                                                       bias_scale0=s0, bias_scale1=s1, row_flags=self.flags))
         self._timed("splice_fwd", lambda: L.splice_fwd(self.sp, self.Y, self.emb))
         return self.emb, self.mask, self.labels_out
 
     def backward(self, allreduce: bool = True):
         g = self.bucket
-        self._timed("splice_bwd", lambda: L.splice_bwd(self.sp, self.d_emb, self.dY))
-        xs, dws, al = [], [], []
+        B, N, P = self.shape.batch, self.N, self.shape.prompt_len
+        dws, al = [], []
         if self.use_a:
-            xs.append(self.A[:, :self.Ka]); dws.append(g["audio_connector.linear.weight"]); al.append(self.sa)
+            dws.append(g["audio_connector.linear.weight"]); al.append(self.sa)
         if self.use_v:
-            xs.append(self.A[:, self.Ka:]); dws.append(g["video_connector.linear.weight"]); al.append(self.sv)
-        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(self.dY, xs, dws, al))
-        self._timed("colsum", lambda: L.colsum(
-            self.dY, g["audio_connector.linear.bias"] if self.use_a else None,
-            g["video_connector.linear.bias"] if self.use_v else None, self.colsum_ws, row_flags=self.flags,
-            alpha0=self.sa, alpha1=self.sv))
+            dws.append(g["video_connector.linear.weight"]); al.append(self.sv)
+        dba = g["audio_connector.linear.bias"] if self.use_a else None
+        dbv = g["video_connector.linear.bias"] if self.use_v else None
+        if self.direct:
+            xs = ([self.audio.view(B, N, self.Ka)] if self.use_a else []) + \
+                 ([self.video.view(B, N, self.Kv)] if self.use_v else [])
+            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(self.d_emb, xs, dws, al, dy_row_base=P))
+            self._timed("colsum", lambda: L.colsum(self.d_emb, dba, dbv, self.colsum_ws, alpha0=self.sa,
+                                                   alpha1=self.sv, dy_row_base=P, sum_rows=N))
+        else:
+            self._timed("splice_bwd", lambda: L.splice_bwd(self.sp, self.d_emb, self.dY))
+            xs = ([self.A[:, :self.Ka]] if self.use_a else []) + ([self.A[:, self.Ka:]] if self.use_v else [])
+            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(self.dY, xs, dws, al))
+            self._timed("colsum", lambda: L.colsum(self.dY, dba, dbv, self.colsum_ws, row_flags=self.flags,
+                                                   alpha0=self.sa, alpha1=self.sv))
         if allreduce:
             g.allreduce()
         return g

@@ -94,11 +94,13 @@ AVC_API int avc_proj_bwd_dw(const avc_mat* dy /* bf16 [b][rows][H] */, int32_t d
                     const avc_mat* x /* [nseg] bf16 */, const avc_mat* dw /* [nseg] fp32 [H, K_s] */,
                     const float* alpha /* [nseg] */, void* stream);
 
-/* ---- bias gradient: deterministic two-pass column sum over flagged rows ------------------------- */
+/* ---- bias gradient: deterministic two-pass column sum over flagged rows -------------------------
+ * out_i[c] = alpha_i * sum_{b, r < sum_rows : flag_i(b, r)} dY[b, dy_row_base + r, c]      (db = sum dY)
+ * flags: row_flags[b * sum_rows + r] bit i, or (r < flag_rows_i) when row_flags is NULL. */
 AVC_API size_t avc_colsum_workspace_bytes(int32_t cols);
-AVC_API int avc_colsum(const avc_mat* dy /* bf16 */, const uint8_t* row_flags, int32_t flag_rows0,
-               int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1,
-               void* workspace, void* stream);
+AVC_API int avc_colsum(const avc_mat* dy /* bf16 */, int32_t dy_row_base, int32_t sum_rows,
+               const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, float alpha0,
+               float alpha1, float* out0, float* out1, void* workspace, void* stream);
 
 /* ---- weight pack: W_bf16 = bf16(alpha * W_fp32) (folds fusion_scale into the projector) -------- */
 AVC_API int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows,

@@ -274,3 +274,50 @@ def test_no_cpu_fallback(avc, cuda_dev):
         avc.fused_connector(torch.zeros(1, 4, 8), None, w, b, None, None, plan)
     with pytest.raises(avc._lib.ConnectorError):
         avc.ClipWhisperModel(device="cpu", _provided_llm=object(), _provided_tokenizer=object())
+
+
+@pytest.mark.parametrize("modality,ka,kv", [("both", 4, 2), ("audio", 2, 1), ("video", 1, 1), ("both", 1, 1)])
+def test_step_engine_fused_equals_unfused_and_oracle(avc, cuda_dev, modality, ka, kv):
+    """engine.ConnectorStep (what bench.py times): the gather-free step (GEMM reads the tower outputs and
+    d(inputs_embeds) in place) against the gather / splice-bwd step and against the CPU oracle."""
+    from audio_visual_llm_b200.engine import ConnectorStep, StepShape
+
+    shape = StepShape(batch=3, audio_frames=40 * ka, video_frames=40 * kv, audio_dim=64, video_dim=32, hidden=128,
+                      prompt_len=5, vocab=50, label_len=30)
+    plan = avc.FusePlan(modality=modality, fusion="concat", audio_stride=ka, video_stride=kv, max_seq_len=4096)
+    fused = ConnectorStep(shape, plan, cuda_dev, seed=3, fuse_gather=True)
+    plain = ConnectorStep(shape, plan, cuda_dev, seed=3, fuse_gather=False)
+    assert fused.direct and not plain.direct
+    outs = []
+    for eng in (fused, plain):
+        emb, mask, lab = eng.forward()
+        g = eng.backward(allreduce=False)
+        torch.cuda.synchronize()
+        assert int(eng.status.item()) == 0
+        outs.append((emb.clone(), mask.clone(), lab.clone(), {k: v.clone() for k, v in g.views.items()}))
+    (e1, m1, l1, g1), (e2, m2, l2, g2) = outs
+    assert torch.equal(e1, e2) and torch.equal(m1, m2) and torch.equal(l1, l2)  # same k-block order: same bits
+    for k in g1:
+        assert rel_err(g1[k], g2[k]) <= 1e-5, k  # reduction split per sample vs packed: fp32 reassociation only
+    # oracle on the same (bf16-rounded) inputs
+    eng = fused
+    f32 = lambda t: None if t is None else t.detach().float().cpu()
+    spec = O.ConnectorSpec(modality=modality, fusion="concat", audio_stride=ka, video_stride=kv, max_seq_len=4096)
+    wa = f32(eng.wa) if eng.use_a else torch.zeros(128, 8)
+    wv = f32(eng.wv) if eng.use_v else torch.zeros(128, 8)
+    ba = f32(eng.ba) if eng.use_a else torch.zeros(128)
+    bv = f32(eng.bv) if eng.use_v else torch.zeros(128)
+    ids = eng.input_ids.cpu()
+    tok, _ = O.connector_tokens(f32(eng.audio), f32(eng.video), wa, ba, wv, bv, spec)
+    emb_r, mask_r, lab_r = O.splice_tokens(tok, ids, eng.placeholder_id, f32(eng.embed_table), 0, spec,
+                                           labels=eng.labels_in.cpu())
+    P = shape.prompt_len
+    assert_close(e1[:, P:], emb_r[:, P:], "AV rows")
+    assert torch.equal(e1[:, :P].cpu(), emb_r[:, :P].to(torch.bfloat16))
+    assert torch.equal(m1.cpu(), mask_r) and torch.equal(l1.cpu(), lab_r)
+    grads = O.connector_grads(f32(eng.audio), f32(eng.video), wa, ba, wv, bv, spec, f32(eng.d_emb)[:, P:])
+    names = ["audio_connector.linear.weight", "audio_connector.linear.bias", "video_connector.linear.weight",
+             "video_connector.linear.bias"]
+    for n, gr in zip(names, grads):
+        if n in g1:
+            assert_close(g1[n], gr, n)
