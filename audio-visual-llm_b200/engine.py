@@ -209,3 +209,56 @@ class ConnectorStep:
             self.video.copy_(video_h, non_blocking=True)
         self.input_ids.copy_(ids_h, non_blocking=True)
         self.labels_in.copy_(labels_h, non_blocking=True)
+
+
+class HostFeeder:
+    """Double-buffered host -> device input pipeline for the connector step.
+
+    The reference trainer copies each batch to the device synchronously right before the step
+    (`.to(device)`, clip_whisper_trainer.py:655-657, pin_memory=False).  Here the batch for step i+1 is copied from
+    PINNED host memory on a side stream while step i computes; a slot is only overwritten after the step that read
+    it (forward and backward) has finished on the compute stream.
+    """
+
+    def __init__(self, device, slots: int = 2):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict(bufs=None, ready=torch.cuda.Event(), free=None) for _ in range(slots)]
+        self.head = 0   # next slot to fill
+        self.tail = 0   # next slot to hand out
+        self.bytes_per_batch = 0
+
+    def prefetch(self, host_tensors):
+        """Start the H2D copy of one batch (a sequence of pinned CPU tensors, None entries allowed)."""
+        slot = self.slots[self.head % len(self.slots)]
+        self.head += 1
+        if slot["bufs"] is None:
+            slot["bufs"] = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                            for t in host_tensors]
+        with torch.cuda.stream(self.copy_stream):
+            if slot["free"] is not None:
+                self.copy_stream.wait_event(slot["free"])  # the step that last read this slot is done
+            nbytes = 0
+            for dst, src in zip(slot["bufs"], host_tensors):
+                if src is None:
+                    continue
+                if not src.is_pinned():
+                    raise ValueError("HostFeeder needs pinned host tensors (torch.Tensor.pin_memory())")
+                dst.copy_(src, non_blocking=True)
+                nbytes += src.nbytes
+            slot["ready"].record(self.copy_stream)
+        self.bytes_per_batch = nbytes
+
+    def take(self):
+        """Device tensors of the oldest prefetched batch; the current stream waits for its copy."""
+        slot = self.slots[self.tail % len(self.slots)]
+        self.tail += 1
+        torch.cuda.current_stream().wait_event(slot["ready"])
+        self._last = slot
+        return slot["bufs"]
+
+    def release(self):
+        """Call after the step (forward + backward) that consumed the last `take()` has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._last["free"] = ev

@@ -306,17 +306,22 @@ def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
     h2d = audio_h.nbytes + video_h.nbytes + ids_h.nbytes + labels_h.nbytes
     d2h = mask_h.nbytes + lab_h.nbytes + db_h.nbytes
 
-    def step():
+    from audio_visual_llm_b200.engine import HostFeeder
+
+    feeder = HostFeeder(dev)
+    batch = (audio_h, video_h, ids_h, labels_h)
+
+    def step(last):
         for p in (wa, ba, wv, bv):
             p.grad = None
-        a = audio_h.to(dev, non_blocking=True)
-        v = video_h.to(dev, non_blocking=True)
-        ids = ids_h.to(dev, non_blocking=True)
-        lab_in = labels_h.to(dev, non_blocking=True)
-        emb, mask, lab = pkg.fused_connector(a, v, wa, ba, wv, bv, plan, input_ids=ids,
-                                             placeholder_id=eng.placeholder_id, embed_table=eng.embed_table,
-                                             labels=lab_in, out_dtype=torch.bfloat16)
+        a, v, ids, lab_in = feeder.take()           # this step's inputs (H2D issued one step earlier, inside the region)
+        if not last:
+            feeder.prefetch(batch)                  # next step's H2D overlaps this step's kernels
+        emb, mask, lab = pkg.fused_connector(a, v, wa, ba, wv, bv, plan, prompt_ids=ids[:, :s.prompt_len],
+                                             embed_table=eng.embed_table, labels=lab_in,
+                                             placeholder_id=eng.placeholder_id, out_dtype=torch.bfloat16)
         emb.backward(eng.d_emb)
+        feeder.release()
         if world > 1:
             for p in (wa, ba, wv, bv):
                 dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
@@ -325,15 +330,18 @@ def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
         db_h[0].copy_(ba.grad, non_blocking=True)
         db_h[1].copy_(bv.grad, non_blocking=True)
 
-    for _ in range(max(3, args.warmup)):
-        step()
+    def run(n):
+        feeder.prefetch(batch)                      # first batch: its copy is inside the timed region too
+        for i in range(n):
+            step(i == n - 1)
+
+    run(max(3, args.warmup))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        step()
+    run(args.steps)
     t1.record()
     if world > 1:
         dist.barrier()
@@ -346,7 +354,8 @@ def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
     ms_step = ms / args.steps
     return {"value": eng.fused_tokens * world / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "api": "fused_connector(...) + emb.backward(dLLM) from pinned host tensors"}
+            "api": "HostFeeder (pinned host -> device, double-buffered on a copy stream) -> fused_connector(...) -> "
+                   "emb.backward(dLLM) -> D2H of masks / labels / bias grads; every step's H2D is inside the timed region"}
 
 
 if __name__ == "__main__":
