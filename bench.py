@@ -146,6 +146,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if "AVC_KEEP_NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     w = WORKLOAD
