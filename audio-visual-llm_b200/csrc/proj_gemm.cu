@@ -402,7 +402,9 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
   args.full_tiles = num_tiles;
   args.tail_split = 1;
   args.l2_hints = env_int("AVC_GEMM_L2_HINTS", 1);
-  args.group_m = env_int("AVC_GEMM_GROUP_M", 8);
+  // forward: M-major order streams each activation panel once while the (L2-resident, evict-last) weights are
+  // re-read; dW: 8 x ~9 tile groups per round cut the panel re-reads (measured DRAM bytes: profiles/)
+  args.group_m = env_int("AVC_GEMM_GROUP_M", mode == GEMM_TN ? 1 : 8);
   if (args.group_m < 1) args.group_m = 1;
   if (args.group_m > args.num_m_blocks) args.group_m = args.num_m_blocks;
   const int leftover = num_tiles % workers;
