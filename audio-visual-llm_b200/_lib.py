@@ -44,7 +44,7 @@ class AvcSplice(C.Structure):
         ("tok_offset", C.c_void_p), ("embed_table", C.c_void_p), ("vocab", C.c_int64),
         ("attention_mask", C.c_void_p), ("mask_mode", C.c_int32), ("label_mode", C.c_int32),
         ("labels_in", C.c_void_p), ("label_len", C.c_int32), ("elem_size", C.c_int32),
-        ("labels_out", C.c_void_p), ("status", C.c_void_p),
+        ("labels_out", C.c_void_p), ("status", C.c_void_p), ("av_rows_in_place", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -177,13 +177,14 @@ def pack_weight(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> Non
 
 def make_splice(input_ids: torch.Tensor, placeholder_id: int, pad_id: int, hidden: int, tokens_per_sample: int = 0,
                 tok_offset=None, embed_table=None, attention_mask=None, mask_mode: int = 0, label_mode: int = 0,
-                labels_in=None, labels_out=None, status=None, elem_size: int = 2) -> AvcSplice:
+                labels_in=None, labels_out=None, status=None, elem_size: int = 2,
+                av_rows_in_place: bool = False) -> AvcSplice:
     b, s = input_ids.shape
     sp = AvcSplice(
         input_ids.data_ptr(), placeholder_id, pad_id, b, s, hidden, tokens_per_sample, _ptr(tok_offset),
         _ptr(embed_table), 0 if embed_table is None else embed_table.shape[0], _ptr(attention_mask), mask_mode,
         label_mode, _ptr(labels_in), 0 if labels_in is None else labels_in.shape[1], elem_size, _ptr(labels_out),
-        _ptr(status))
+        _ptr(status), 1 if av_rows_in_place else 0, 0)
     # the struct only holds raw pointers: keep the tensors alive as long as the descriptor is
     sp._keep = (input_ids, tok_offset, embed_table, attention_mask, labels_in, labels_out, status)
     return sp

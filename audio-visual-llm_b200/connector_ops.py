@@ -179,7 +179,13 @@ class _FusedConnectorFn(torch.autograd.Function):
         ws = ([wa] if use_a else []) + ([wv] if use_v else [])
         wp = pack_projector(ws, ([sa] if use_a else []) + ([sv] if use_v else []))
         out_dtype = st["out_dtype"]
-        Y = torch.empty(M, H, dtype=out_dtype, device=dev)
+        ids = st["input_ids"]
+        S = ids.shape[1]
+        emb = torch.empty(B, S, H, dtype=out_dtype, device=dev)
+        # `[prompt | AV]` layout built by fused_connector: the GEMM epilogue writes the projected rows straight into
+        # the AV region of inputs_embeds (scatter output) and the splice kernel only adds text rows and masks
+        in_place = bool(st["uniform_layout"] and M)
+        Y = emb[:, S - N:, :] if in_place else torch.empty(M, H, dtype=out_dtype, device=dev)
         if use_a and use_v:
             b0, b1, s0, s1 = ba, bv, sa, sv
         elif use_a:
@@ -207,9 +213,6 @@ class _FusedConnectorFn(torch.autograd.Function):
                 # 2. projector: one GEMM over [a ; v]
                 L.proj_fwd([A], [wp], Y, bias0=b0, bias1=b1, bias_scale0=s0, bias_scale1=s1, row_flags=flags)
         # 3. splice into the LLM input-embedding sequence + masks
-        ids = st["input_ids"]
-        S = ids.shape[1]
-        emb = torch.empty(B, S, H, dtype=out_dtype, device=dev)
         mask = torch.empty(B, S, dtype=torch.int64, device=dev)
         want_labels = st["labels"] is not None or plan.label_mode == 1
         labels_out = torch.empty(B, S, dtype=torch.int64, device=dev) if want_labels else None
@@ -217,8 +220,9 @@ class _FusedConnectorFn(torch.autograd.Function):
         sp = L.make_splice(ids, st["placeholder_id"], st["pad_id"], H, tokens_per_sample=N,
                            tok_offset=st["tok_offset"], embed_table=st["embed_table"], attention_mask=mask,
                            mask_mode=plan.mask_mode, label_mode=plan.label_mode, labels_in=st["labels"],
-                           labels_out=labels_out, status=status, elem_size=4 if out_dtype == torch.float32 else 2)
-        L.splice_fwd(sp, Y if M else None, emb)
+                           labels_out=labels_out, status=status, elem_size=4 if out_dtype == torch.float32 else 2,
+                           av_rows_in_place=in_place)
+        L.splice_fwd(sp, None if (in_place or not M) else Y, emb)
         ctx.save_for_backward(*xs)
         ctx.flags = flags
         ctx.sp = sp

@@ -190,15 +190,26 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   memset(&g, 0, sizeof(g));
   g.nseg = nseg;
   const int cg = avc::gemm_cta_group();
-  g.m_tiles_per_batch = static_cast<int>(ceil_div(y->rows, avc::GEMM_BM * cg));
-  g.num_m_blocks = static_cast<int>(y->batches) * g.m_tiles_per_batch;
+  // scatter mode: the operand rows are packed [B*N, K] while Y is a strided [B][N][H] region (e.g. the AV rows of
+  // inputs_embeds): M tiles run over the packed rows and the epilogue splits boxes at sample boundaries
+  const bool scatter = a[0].batches == 1 && y->batches > 1;
+  const int64_t m_rows = scatter ? a[0].rows : y->rows;
+  const int64_t m_batches = scatter ? 1 : y->batches;
+  if (scatter && row_flags == nullptr && (flag_rows0 < m_rows || flag_rows1 < m_rows) && (bias0 || bias1))
+    return fail(AVC_ERR_INVALID, "proj_fwd: analytic row flags are per packed row in scatter mode; pass row_flags");
+  g.m_tiles_per_batch = static_cast<int>(ceil_div(m_rows, avc::GEMM_BM * cg));
+  g.num_m_blocks = static_cast<int>(m_batches) * g.m_tiles_per_batch;
+  g.scatter_rows = scatter ? static_cast<int>(y->rows) : 0;
+  g.scatter_batches = scatter ? static_cast<int>(y->batches) : 0;
   g.bn = avc::pick_gemm_bn(g.num_m_blocks, &N, 1, di.num_sms / cg);
   for (int s = 0; s < nseg; ++s) {
     if (a[s].cols != w[s].cols)
       return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: A has K=%lld but W has K=%lld", s,
                   static_cast<long long>(a[s].cols), static_cast<long long>(w[s].cols));
     if (w[s].rows != N) return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: W rows != N", s);
-    if (a[s].batches != y->batches) return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: batch mismatch", s);
+    if (a[s].batches != y->batches && !(a[s].batches == 1 && a[s].rows == y->batches * y->rows))
+      return fail(AVC_ERR_INVALID, "proj_fwd: segment %d: batch mismatch", s);
+    if (s > 0 && a[s].batches != a[0].batches) return fail(AVC_ERR_INVALID, "proj_fwd: segments disagree on batching");
     if (a[s].cols % 8 != 0) return fail(AVC_ERR_INVALID, "proj_fwd: K must be a multiple of 8");
     if (int rc = make_map3d(&g.ma[s], a[s].ptr, false, a[s].cols, a[s].rows, a[s].batches, a[s].row_stride,
                             a[s].batch_stride, avc::GEMM_BK, avc::GEMM_BM, "proj_fwd A"))
@@ -212,7 +223,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
                           y->batch_stride, y_is_fp32 ? 32 : 64, 32, "proj_fwd Y"))
     return rc;
   g.num_n_blocks = static_cast<int>(ceil_div(N, g.bn));
-  g.d_rows = static_cast<int>(y->rows);
+  g.d_rows = static_cast<int>(m_rows);
   g.d_cols[0] = static_cast<int>(N);
   g.d_cols[1] = static_cast<int>(N);
   g.bias0 = bias0;
@@ -351,6 +362,7 @@ static int fill_splice(const avc_splice* s, avc::SpliceArgs* k) {
   k->labels_out = s->labels_out;
   k->label_mode = s->label_mode;
   k->status = s->status;
+  k->av_in_place = s->av_rows_in_place;
   return AVC_OK;
 }
 

@@ -45,6 +45,8 @@ struct GemmArgs {
   const uint8_t* row_flags;  // packed-row mode: flags[batch * d_rows + row]; nullptr: analytic
   int flag_rows0;            // analytic: bit0 = row < flag_rows0
   int flag_rows1;            // analytic: bit1 = row < flag_rows1
+  int scatter_rows;          // TN: > 0: A rows are packed [batches * scatter_rows] while the output map is
+  int scatter_batches;       //     [scatter_batches][scatter_rows][N] (epilogue writes into a strided region)
   float alpha[2];            // NT: output scale per segment
   float bias_scale[2];       // TN: bias multipliers (fusion_scale folded into the bias)
   int act;                   // 0 = identity, 1 = GELU (erf form)
@@ -101,6 +103,7 @@ struct SpliceArgs {
   int64_t* labels_out;        // [B, S] may be null
   int label_mode;             // 0 = reference (pad->-100, truncate / right-pad -100), 1 = causal-LM
   int32_t* status;            // device int: set to nonzero on malformed input (placeholder count)
+  int av_in_place;            // fwd: placeholder rows were already written by the GEMM epilogue: leave them
 };
 cudaError_t launch_splice_fwd(const SpliceArgs& args, int num_sms, cudaStream_t stream);
 cudaError_t launch_splice_bwd(const SpliceArgs& args, int num_sms, cudaStream_t stream);

@@ -355,8 +355,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (out_row0 < args.d_rows && col < ncols)
-            tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
+          if (out_row0 < args.d_rows && col < ncols) {
+            if (MODE == GEMM_TN && args.scatter_rows > 0) {
+              // packed rows m = b * scatter_rows + j go to row j of batch entry b of the output map (the AV region
+              // of inputs_embeds); a 32-row box that straddles samples is stored once per sample, TMA clipping the
+              // rows that fall outside [0, scatter_rows) of that sample
+              int b = out_row0 / args.scatter_rows;
+              for (int j = out_row0 - b * args.scatter_rows; j > -32 && b < args.scatter_batches;
+                   j -= args.scatter_rows, ++b)
+                tma_store_3d(&args.md[seg], sbuf, col, j, b);
+            } else {
+              tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
+            }
+          }
           bulk_commit();
         }
         buf ^= 1u;

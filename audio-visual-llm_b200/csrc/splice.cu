@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SP_THREADS) splice_kernel(const __grid_constan
         src = a.embed_table + id * a.row_bytes;
       }
       s_src[lane] = src;
-      s_dst[lane] = in ? emb_row : nullptr;
+      s_dst[lane] = (in && !(a.av_in_place && has_row)) ? emb_row : nullptr;
       if (in) {
         if (a.attention_mask != nullptr) {
           int64_t mval = 1;

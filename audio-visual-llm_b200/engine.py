@@ -101,6 +101,12 @@ class ConnectorStep:
                                 embed_table=self.embed_table, attention_mask=self.mask, mask_mode=p.mask_mode,
                                 label_mode=p.label_mode, labels_in=self.labels_in, labels_out=self.labels_out,
                                 status=self.status)
+        # same descriptor for the fused step: the GEMM epilogue has already written the AV rows of inputs_embeds
+        self.sp_text = L.make_splice(self.input_ids, self.placeholder_id, 0, H, tokens_per_sample=self.N,
+                                     embed_table=self.embed_table, attention_mask=self.mask, mask_mode=p.mask_mode,
+                                     label_mode=p.label_mode, labels_in=self.labels_in, labels_out=self.labels_out,
+                                     status=self.status, av_rows_in_place=True)
+        self.emb_av = self.emb[:, s.prompt_len:, :]  # [B, N, H] view: where the projected rows live
         # Gather-free ("direct") mode: when every stream is dense and its frame count divides by the stride, the
         # stacked operand is a free reshape of the tower output, so the GEMMs read it in place (two K segments) and
         # the backward reads d(inputs_embeds) in place (the `[prompt | AV]` layout puts the AV rows of sample b at
@@ -162,8 +168,10 @@ class ConnectorStep:
             xs = ([self.audio.view(self.M, self.Ka)] if self.use_a else []) + \
                  ([self.video.view(self.M, self.Kv)] if self.use_v else [])
             wsegs = ([self.wp[:, :self.Ka]] if self.use_a else []) + ([self.wp[:, self.Ka:]] if self.use_v else [])
-            self._timed("proj_fwd", lambda: L.proj_fwd(xs, wsegs, self.Y, bias0=b0, bias1=b1, bias_scale0=s0,
+            self._timed("proj_fwd", lambda: L.proj_fwd(xs, wsegs, self.emb_av, bias0=b0, bias1=b1, bias_scale0=s0,
                                                        bias_scale1=s1))
+            self._timed("splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
+            return self.emb, self.mask, self.labels_out
         else:
             self._timed("proj_fwd", lambda: L.proj_fwd([self.A], [self.wp], self.Y, bias0=b0, bias1=b1,
                                                        bias_scale0=s0, bias_scale1=s1, row_flags=self.flags))

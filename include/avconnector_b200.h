@@ -79,6 +79,9 @@ AVC_API int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t
 /* ---- projector forward (tensor-core bound, tcgen05 + TMEM + TMA) -------------------------------
  * Y[b, r, :] = act( sum_s A_s[b, r, :] . W_s^T  + flag0(b,r) * bias_scale0 * bias0 + flag1(b,r) * bias_scale1 * bias1 )
  * flags come from row_flags (packed rows) or, if NULL, flag_i = (r < flag_rows_i).
+ * Scatter output: when every A_s is packed ([B*N, K_s], batches = 1) and y has batches = B, rows = N, packed row
+ * m = b*N + j is written to y[b, j, :] -- y may be the AV region of inputs_embeds (ptr = &emb[0, P, 0],
+ * batch_stride = S*H), which fuses the splice of the projected rows into the GEMM epilogue.
  * Replaces SimpleModalityConnector.forward x2 + weighted sum (modality_connector.py:43-44,
  * clip_whisper_model.py:434) through W = [fs*Wa | (1-fs)*Wv], bias0 = fs*ba, bias1 = (1-fs)*bv. */
 AVC_API int avc_proj_fwd(int32_t nseg, const avc_mat* a /* [nseg] bf16 */, const avc_mat* w /* [nseg] bf16 [N, K_s] */,
@@ -133,6 +136,9 @@ typedef struct avc_splice {
   int32_t elem_size;          /* bytes per element of y / embed_table / inputs_embeds: 2 (bf16) or 4 (fp32); 0 = 2 */
   int64_t* labels_out;        /* [batch, seq] or NULL */
   int32_t* status;            /* device int32 or NULL */
+  int32_t av_rows_in_place;   /* fwd: 1 = the placeholder rows of inputs_embeds were already written by
+                                 avc_proj_fwd (scatter output): only text rows and masks are produced */
+  int32_t reserved;
 } avc_splice;
 
 AVC_API int avc_splice_fwd(const avc_splice* s, const void* y /* bf16 [M, H] */, void* inputs_embeds,
