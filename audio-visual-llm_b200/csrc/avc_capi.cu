@@ -199,6 +199,10 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
     return fail(AVC_ERR_INVALID, "proj_fwd: analytic row flags are per packed row in scatter mode; pass row_flags");
   g.m_tiles_per_batch = static_cast<int>(ceil_div(m_rows, avc::GEMM_BM * cg));
   g.num_m_blocks = static_cast<int>(m_batches) * g.m_tiles_per_batch;
+  if (scatter)
+    if (int rc = make_map3d(&g.md_row, y->ptr, y_is_fp32 != 0, N, y->rows, y->batches, y->row_stride,
+                            y->batch_stride, y_is_fp32 ? 32 : 64, 1, "proj_fwd Y (row box)"))
+      return rc;
   g.scatter_rows = scatter ? static_cast<int>(y->rows) : 0;
   g.scatter_batches = scatter ? static_cast<int>(y->batches) : 0;
   g.bn = avc::pick_gemm_bn(g.num_m_blocks, &N, 1, di.num_sms / cg);

@@ -20,6 +20,7 @@ struct GemmArgs {
   CUtensorMap ma[2];  // TN: A operand per K segment.        NT: ma[0] = dY  ([batch][rows][m])
   CUtensorMap mb[2];  // TN: B operand (weights) per K seg.  NT: X per output segment ([batch][rows][n])
   CUtensorMap md[2];  // TN: md[0] = output.                 NT: output per segment
+  CUtensorMap md_row; // TN scatter output: same tensor as md[0] with a one-row box (sample-straddling boxes)
   int num_m_blocks;
   int num_n_blocks;
   int bn;  // N tile of this launch: 64 | 128 | 192 | 256 (B tensor-map box rows / atoms must match)

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       for (int c = 0; c < nchunk; ++c) {
         const int col = out_col0 + c * COLS;
         // the store issued from this staging buffer two chunks ago must have finished reading it
-        if (lane == 0) bulk_wait_read<1>();
+        if (lane == 0 || (MODE == GEMM_TN && args.scatter_rows > 0)) bulk_wait_read<1>();
         __syncwarp();
         const uint32_t sbuf = s_epi + (ew * 2 + buf) * EPI_BUF_BYTES;
         const uint32_t srow = sbuf + lane * 128;
@@ -354,20 +354,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (MODE == GEMM_TN && args.scatter_rows > 0) {
+          // packed rows m = b * scatter_rows + j go to row j of batch entry b of the output map (the AV region of
+          // inputs_embeds).  A 32-row box inside one sample is one TMA store (rows past the last sample's end are
+          // clipped); a box that straddles a sample boundary is stored row by row, one 128-byte TMA store per lane
+          // (TMA stores may run past the end of a dimension but must not start at a negative coordinate).
+          const int sr = args.scatter_rows;
+          const int b0 = out_row0 / sr;
+          const int j0 = out_row0 - b0 * sr;
           if (out_row0 < args.d_rows && col < ncols) {
-            if (MODE == GEMM_TN && args.scatter_rows > 0) {
-              // packed rows m = b * scatter_rows + j go to row j of batch entry b of the output map (the AV region
-              // of inputs_embeds); a 32-row box that straddles samples is stored once per sample, TMA clipping the
-              // rows that fall outside [0, scatter_rows) of that sample
-              int b = out_row0 / args.scatter_rows;
-              for (int j = out_row0 - b * args.scatter_rows; j > -32 && b < args.scatter_batches;
-                   j -= args.scatter_rows, ++b)
-                tma_store_3d(&args.md[seg], sbuf, col, j, b);
-            } else {
-              tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
+            if (j0 + 32 <= sr || b0 == args.scatter_batches - 1) {
+              if (lane == 0) tma_store_3d(&args.md[seg], sbuf, col, j0, b0);
+            } else if (my_row < args.d_rows) {
+              const int bb = my_row / sr;
+              tma_store_3d(&args.md_row, srow, col, my_row - bb * sr, bb);
             }
           }
+          bulk_commit();  // every lane keeps its own (possibly empty) bulk-group sequence in scatter mode
+        } else if (lane == 0) {
+          if (out_row0 < args.d_rows && col < ncols) tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
           bulk_commit();
         }
         buf ^= 1u;
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
-    if (lane == 0) bulk_wait_all<0>();
+    if (lane == 0 || (MODE == GEMM_TN && args.scatter_rows > 0)) bulk_wait_all<0>();
     __syncwarp();
   }
 
