@@ -213,6 +213,7 @@ def main():
                    "launches_per_step": eng2.launches_per_step}
         for n in ("gather", "splice_bwd"):
             kernel_ms.setdefault(n, k2[n])
+        kernel_ms["splice_fwd_unfused"] = k2["splice_fwd"]
         del eng2
         torch.cuda.empty_cache()
     if world > 1:
@@ -258,7 +259,10 @@ def main():
     kernels = {
         "gather (stand-alone, unfused step)": hbm("gather", eng.gather_bytes()),
         "proj_fwd": tens("proj_fwd"),
-        "splice_fwd": hbm("splice_fwd", eng.splice_bytes()),
+        ("splice_fwd (text rows + masks; AV rows are written by the GEMM epilogue)" if eng.direct else "splice_fwd"):
+            hbm("splice_fwd", (4 * shape.batch * shape.prompt_len * shape.hidden + 16 * shape.batch * eng.S)
+                if eng.direct else eng.splice_bytes()),
+        "splice_fwd (stand-alone, unfused step)": hbm("splice_fwd_unfused", eng.splice_bytes()),
         "splice_bwd (stand-alone, unfused step)": hbm("splice_bwd", 4 * eng.M * shape.hidden),
         "proj_bwd_dw": tens("proj_bwd_dw"),
         "colsum": hbm("colsum", 2 * eng.M * shape.hidden),
@@ -280,7 +284,8 @@ def main():
         "dtype": "bf16", "data": "synthetic",
         "config": {**{k: v for k, v in WORKLOAD.items()},
                    "global_batch": w["batch_per_gpu"] * world, "fused_tokens_per_step": eng.fused_tokens * world,
-                   "parallelism": f"dp{world}", "step": ("fused: tower outputs -> 2-segment GEMM -> splice; dW GEMM and bias sums read d(inputs_embeds) in place"
+                   "parallelism": f"dp{world}", "step": ("fused: tower outputs -> 2-segment GEMM whose epilogue writes the AV rows of inputs_embeds -> text rows + masks; "
+                                                        "dW GEMM and bias sums read d(inputs_embeds) in place"
                                                        if eng.direct else "gather -> GEMM -> splice; splice-bwd -> dW GEMM"),
                    "collective": "projector-grad all-reduce (NCCL avg, 100.7 MB fp32)" if world > 1 else "none",
                    "l2": "no flush: one step streams ~0.9 GB (features, A, W, Y, embeds, grads) >> 126 MB L2"},
