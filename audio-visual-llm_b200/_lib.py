@@ -18,7 +18,7 @@ AVC_ABI_VERSION = 1
 EXPORTS = (
     "avc_abi_version", "avc_last_error", "avc_device_check", "avc_gather_fwd", "avc_proj_fwd",
     "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",
-    "avc_splice_bwd", "avc_row_resample",
+    "avc_splice_bwd", "avc_row_resample", "avc_sumsq_workspace_bytes", "avc_sumsq", "avc_adamw_step",
 )
 
 
@@ -209,3 +209,33 @@ def row_resample(x: torch.Tensor, out: torch.Tensor, row_ptr: torch.Tensor, col_
         C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int32(es), C.c_int32(x.shape[0]),
         C.c_int32(x.shape[1]), C.c_int32(out.shape[1]), C.c_int32(x.shape[2]), C.c_void_p(row_ptr.data_ptr()),
         C.c_void_p(col_idx.data_ptr()), C.c_void_p(weight.data_ptr()), stream_ptr()))
+
+
+def sumsq_workspace(device) -> torch.Tensor:
+    lib = load()
+    lib.avc_sumsq_workspace_bytes.restype = C.c_size_t
+    return torch.empty(lib.avc_sumsq_workspace_bytes() // 4, dtype=torch.float32, device=device)
+
+
+def sumsq(x: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, accumulate: bool = False) -> None:
+    """out[0] (+)= sum(x^2) over a contiguous fp32 tensor, deterministic."""
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("sumsq needs a contiguous fp32 tensor")
+    check(load().avc_sumsq(C.c_void_p(x.data_ptr()), C.c_int64(x.numel()), C.c_void_p(out.data_ptr()),
+                           C.c_void_p(workspace.data_ptr()), C.c_int32(1 if accumulate else 0), stream_ptr()))
+
+
+def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
+               beta1: float, beta2: float, eps: float, weight_decay: float, step: int,
+               grad_scale: Optional[torch.Tensor] = None, clip_sumsq: Optional[torch.Tensor] = None,
+               max_norm: float = 0.0, packed: Optional[torch.Tensor] = None, packed_alpha: float = 1.0) -> None:
+    rows, cols = (param.shape[0], param.shape[1]) if param.dim() == 2 else (1, param.numel())
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("adamw_step needs contiguous fp32 tensors")
+    check(load().avc_adamw_step(
+        C.c_void_p(param.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(exp_avg.data_ptr()),
+        C.c_void_p(exp_avg_sq.data_ptr()), C.c_int64(rows), C.c_int64(cols), C.c_float(lr), C.c_float(beta1),
+        C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_int32(step), C.c_void_p(_ptr(grad_scale)),
+        C.c_void_p(_ptr(clip_sumsq)), C.c_float(max_norm), C.c_void_p(_ptr(packed)), C.c_int64(0 if packed is None else packed.stride(0)), C.c_float(packed_alpha),
+        stream_ptr()))

@@ -3,6 +3,7 @@
 // stream.  Nothing here allocates device memory, synchronises, or falls back to the CPU.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -421,6 +422,56 @@ int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_t batch,
   r.weight = weight;
   cudaError_t e = avc::launch_row_resample(r, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "row_resample launch");
+  return AVC_OK;
+}
+
+size_t avc_sumsq_workspace_bytes(void) { return avc::sumsq_workspace_bytes(); }
+
+int avc_sumsq(const float* x, int64_t n, float* out, void* workspace, int32_t accumulate, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (x == nullptr || out == nullptr || workspace == nullptr || n < 0) return fail(AVC_ERR_INVALID, "sumsq: bad argument");
+  cudaError_t e = avc::launch_sumsq(x, n, out, static_cast<float*>(workspace), accumulate,
+                                    static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "sumsq launch");
+  return AVC_OK;
+}
+
+int avc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t rows, int64_t cols,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                   const float* grad_scale, const float* clip_sumsq, float max_norm, void* packed_bf16,
+                   int64_t packed_ld, float packed_alpha, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr)
+    return fail(AVC_ERR_INVALID, "adamw_step: null pointer");
+  if (step < 1) return fail(AVC_ERR_INVALID, "adamw_step: step counts from 1");
+  avc::AdamWArgs a;
+  memset(&a, 0, sizeof(a));
+  a.param = param;
+  a.grad = grad;
+  a.exp_avg = exp_avg;
+  a.exp_avg_sq = exp_avg_sq;
+  a.rows = rows;
+  a.cols = cols;
+  // scalar prefactors in double, as torch's _single_tensor_adamw computes them on the host
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  a.decay = static_cast<float>(1.0 - static_cast<double>(lr) * weight_decay);
+  a.one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+  a.beta2 = beta2;
+  a.one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+  a.step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  a.bias_correction2_sqrt = static_cast<float>(sqrt(bc2));
+  a.eps = eps;
+  a.grad_scale = grad_scale;
+  a.clip_sumsq = clip_sumsq;
+  a.max_norm = max_norm;
+  a.packed = static_cast<uint8_t*>(packed_bf16);
+  a.packed_ld = packed_ld;
+  a.packed_alpha = packed_alpha;
+  cudaError_t e = avc::launch_adamw(a, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adamw_step launch");
   return AVC_OK;
 }
 

@@ -148,4 +148,29 @@ struct ResampleArgs {
 };
 cudaError_t launch_row_resample(const ResampleArgs& args, cudaStream_t stream);
 
+// Trainer step for the projector parameters (clip_whisper_trainer.py:171-207, 453-464): deterministic
+// sum of squares of the gradient bucket (for the global-norm clip) and AdamW.
+size_t sumsq_workspace_bytes();
+cudaError_t launch_sumsq(const float* x, int64_t n, float* out, float* workspace, int accumulate,
+                         cudaStream_t stream);
+struct AdamWArgs {
+  float* param;            // [rows, cols] fp32, contiguous
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t rows, cols;
+  float decay;             // 1 - lr * weight_decay
+  float one_minus_beta1, beta2, one_minus_beta2;
+  float step_size;         // lr / (1 - beta1^t)
+  float bias_correction2_sqrt;  // sqrt(1 - beta2^t)
+  float eps;
+  const float* grad_scale; // device scalar multiplied into the gradient, may be null
+  const float* clip_sumsq; // device scalar: squared global gradient norm; with max_norm > 0 the gradient is also
+  float max_norm;          //   multiplied by min(1, max_norm / (sqrt(*clip_sumsq) + 1e-6)) (clip_grad_norm_)
+  uint8_t* packed;         // optional bf16 [rows, packed_ld] destination for packed_alpha * param
+  int64_t packed_ld;
+  float packed_alpha;
+};
+cudaError_t launch_adamw(const AdamWArgs& args, cudaStream_t stream);
+
 }  // namespace avc

@@ -169,7 +169,116 @@ __global__ void __launch_bounds__(128) row_resample_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------- trainer step
+constexpr int SQ_BLOCKS = 592;  // 4 x 148
+constexpr int SQ_THREADS = 256;
+
+// deterministic sum of squares: fixed grid, fixed per-thread stride order, fixed tree
+__global__ void __launch_bounds__(SQ_THREADS) sumsq_partial_kernel(const float* __restrict__ x, int64_t n,
+                                                                    float* __restrict__ partial) {
+  __shared__ float red[SQ_THREADS / 32];
+  float s = 0.f;
+  const int64_t nv = n >> 2;
+  const float4* xv = reinterpret_cast<const float4*>(x);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(SQ_THREADS) + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(SQ_BLOCKS) * SQ_THREADS) {
+    const float4 v = __ldg(xv + i);
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float t = x[(nv << 2) + threadIdx.x];
+    s = fmaf(t, t, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < SQ_THREADS / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32) sumsq_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                         int accumulate) {
+  // one warp, fixed order: lane l adds partial[l], partial[l + 32], ... then a fixed shuffle tree
+  float s = 0.f;
+  for (int i = threadIdx.x; i < SQ_BLOCKS; i += 32) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) *out = accumulate ? (*out + s) : s;
+}
+
+// AdamW (torch.optim.AdamW semantics, decoupled weight decay) on a [rows, cols] fp32 parameter, with the gradient
+// pre-scaled by a device scalar (global-norm clip coefficient) and an optional bf16 copy alpha * p written into the
+// packed projector operand for the next forward.
+__global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ AdamWArgs a) {
+  const int64_t groups_per_row = a.cols >> 2;
+  const int64_t total = a.rows * groups_per_row;
+  float gs = a.grad_scale != nullptr ? __ldg(a.grad_scale) : 1.f;
+  if (a.clip_sumsq != nullptr && a.max_norm > 0.f)  // torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))
+    gs *= fminf(1.f, a.max_norm / (sqrtf(__ldg(a.clip_sumsq)) + 1e-6f));
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / groups_per_row;
+    const int64_t c = (g - r * groups_per_row) << 2;
+    const int64_t i = r * a.cols + c;
+    float4 p = *reinterpret_cast<const float4*>(a.param + i);
+    const float4 gr = __ldg(reinterpret_cast<const float4*>(a.grad + i));
+    float4 m = *reinterpret_cast<const float4*>(a.exp_avg + i);
+    float4 v = *reinterpret_cast<const float4*>(a.exp_avg_sq + i);
+    float* pp = &p.x; const float* gp = &gr.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = gp[e] * gs;
+      pp[e] = pp[e] * a.decay;                                   // p *= 1 - lr * weight_decay
+      mp[e] = mp[e] + (gg - mp[e]) * a.one_minus_beta1;          // lerp, as torch does
+      vp[e] = vp[e] * a.beta2 + gg * gg * a.one_minus_beta2;
+      const float denom = sqrtf(vp[e]) / a.bias_correction2_sqrt + a.eps;
+      pp[e] = pp[e] - a.step_size * (mp[e] / denom);
+    }
+    *reinterpret_cast<float4*>(a.param + i) = p;
+    *reinterpret_cast<float4*>(a.exp_avg + i) = m;
+    *reinterpret_cast<float4*>(a.exp_avg_sq + i) = v;
+    if (a.packed != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(p.x * a.packed_alpha, p.y * a.packed_alpha);
+      o.y = pack_bf16x2(p.z * a.packed_alpha, p.w * a.packed_alpha);
+      *reinterpret_cast<uint2*>(a.packed + (r * a.packed_ld + c) * 2) = o;
+    }
+  }
+}
+
 }  // namespace
+
+size_t sumsq_workspace_bytes() { return SQ_BLOCKS * sizeof(float); }
+
+cudaError_t launch_sumsq(const float* x, int64_t n, float* out, float* workspace, int accumulate,
+                         cudaStream_t stream) {
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorMisalignedAddress;
+  sumsq_partial_kernel<<<SQ_BLOCKS, SQ_THREADS, 0, stream>>>(x, n, workspace);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sumsq_final_kernel<<<1, 32, 0, stream>>>(workspace, out, accumulate);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw(const AdamWArgs& a, cudaStream_t stream) {
+  if (a.rows <= 0 || a.cols <= 0) return cudaSuccess;
+  if (a.cols % 4 != 0 || (reinterpret_cast<uintptr_t>(a.param) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(a.grad) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.exp_avg) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(a.exp_avg_sq) & 15) != 0)
+    return cudaErrorMisalignedAddress;
+  if (a.packed != nullptr && ((reinterpret_cast<uintptr_t>(a.packed) & 7) != 0 || a.packed_ld % 4 != 0))
+    return cudaErrorMisalignedAddress;
+  const int64_t total = a.rows * (a.cols >> 2);
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_row_resample(const ResampleArgs& a, cudaStream_t stream) {
   if (a.batch <= 0 || a.dst_rows <= 0) return cudaSuccess;

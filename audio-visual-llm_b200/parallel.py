@@ -29,13 +29,22 @@ class GradBucket:
             offs[name] = (total, n, shape)
             total += (n + align_elems - 1) // align_elems * align_elems  # keep every view 256-byte aligned
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self._pads = []
         for name, (o, n, shape) in offs.items():
             self.views[name] = self.flat[o:o + n].view(*shape)
+            end = (n + align_elems - 1) // align_elems * align_elems
+            if end > n:
+                self._pads.append(self.flat[o + n:o + end])
         self.group = process_group
         self.comm_stream: Optional[torch.cuda.Stream] = None
 
     def __getitem__(self, name: str) -> torch.Tensor:
         return self.views[name]
+
+    def zero_padding(self) -> None:
+        """Alignment gaps between views stay zero so that whole-bucket reductions (norms) see only gradients."""
+        for pad in self._pads:
+            pad.zero_()
 
     def world_size(self) -> int:
         if not (dist.is_available() and dist.is_initialized()):

@@ -156,6 +156,22 @@ AVC_API int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_
                              int32_t dst_rows, int32_t hidden, const int32_t* row_ptr, const int32_t* col_idx,
                              const float* weight, void* stream);
 
+/* ---- trainer step for the projector parameters ----------------------------------------------------
+ * Replaces, for the connector parameters, clip_grad_norm_ + AdamW.step of the reference trainer
+ * (clip_whisper_trainer.py:171-207 param groups / AdamW(betas=(0.9, 0.95), eps=1e-8), :453-464 step).
+ * avc_sumsq: *out (+)= sum x[i]^2, deterministic (fixed grid and reduction order); the caller adds the other
+ *   parameters' contribution and turns the global norm into a clip coefficient kept ON THE DEVICE.
+ * avc_adamw_step: torch.optim.AdamW semantics on one [rows, cols] fp32 tensor; grad is multiplied by *grad_scale
+ *   first, and by min(1, max_norm / (sqrt(*clip_sumsq) + 1e-6)) when clip_sumsq != NULL and max_norm > 0
+ *   (torch.nn.utils.clip_grad_norm_ with the squared global norm kept on the device); optionally writes bf16(packed_alpha * param) into the packed projector operand (row stride
+ *   packed_ld elements), which replaces the per-step avc_pack_weight. */
+AVC_API size_t avc_sumsq_workspace_bytes(void);
+AVC_API int avc_sumsq(const float* x, int64_t n, float* out, void* workspace, int32_t accumulate, void* stream);
+AVC_API int avc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t rows,
+                           int64_t cols, float lr, float beta1, float beta2, float eps, float weight_decay,
+                           int32_t step, const float* grad_scale, const float* clip_sumsq, float max_norm,
+                           void* packed_bf16, int64_t packed_ld, float packed_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
