@@ -10,6 +10,7 @@ from . import _lib  # noqa: F401
 from .connector_ops import FusePlan, fused_connector, linear_project  # noqa: F401
 from .modality_connector import (  # noqa: F401
     BaseModalityConnector,
+    MLPModalityConnector,
     ModalityConnector,
     SimpleModalityConnector,
     create_modality_connector,
@@ -18,7 +19,7 @@ from .clip_whisper_model import ClipWhisperModel  # noqa: F401
 from .seq_adapt import adapt_mask, adaptive_projection  # noqa: F401
 
 __all__ = [
-    "ClipWhisperModel", "ModalityConnector", "SimpleModalityConnector", "BaseModalityConnector",
+    "ClipWhisperModel", "ModalityConnector", "SimpleModalityConnector", "MLPModalityConnector", "BaseModalityConnector",
     "create_modality_connector", "FusePlan", "fused_connector", "linear_project", "adaptive_projection",
     "adapt_mask",
 ]

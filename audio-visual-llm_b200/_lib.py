@@ -19,6 +19,7 @@ EXPORTS = (
     "avc_abi_version", "avc_last_error", "avc_device_check", "avc_gather_fwd", "avc_proj_fwd",
     "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",
     "avc_splice_bwd", "avc_row_resample", "avc_sumsq_workspace_bytes", "avc_sumsq", "avc_adamw_step",
+    "avc_gelu_fwd", "avc_gelu_bwd", "avc_pack_weight_t",
 )
 
 
@@ -239,3 +240,26 @@ def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
         C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_int32(step), C.c_void_p(_ptr(grad_scale)),
         C.c_void_p(_ptr(clip_sumsq)), C.c_float(max_norm), C.c_void_p(_ptr(packed)), C.c_int64(0 if packed is None else packed.stride(0)), C.c_float(packed_alpha),
         stream_ptr()))
+
+
+def gelu_fwd(z: torch.Tensor, out: torch.Tensor, row_flags: Optional[torch.Tensor] = None, flag_bit: int = 1) -> None:
+    """out[r] = flag(r) ? gelu(z[r]) : 0 on bf16 [rows, cols] matrices (columns contiguous)."""
+    check(load().avc_gelu_fwd(C.c_void_p(z.data_ptr()), C.c_int64(z.stride(0)), C.c_void_p(out.data_ptr()),
+                              C.c_int64(out.stride(0)), C.c_int64(z.shape[0]), C.c_int64(z.shape[1]),
+                              C.c_void_p(_ptr(row_flags)), C.c_int32(flag_bit), stream_ptr()))
+
+
+def gelu_bwd(dh: torch.Tensor, z: torch.Tensor, out: torch.Tensor, row_flags: Optional[torch.Tensor] = None,
+             flag_bit: int = 1) -> None:
+    """out[r] = flag(r) ? dh[r] * gelu'(z[r]) : 0."""
+    check(load().avc_gelu_bwd(C.c_void_p(dh.data_ptr()), C.c_int64(dh.stride(0)), C.c_void_p(z.data_ptr()),
+                              C.c_int64(z.stride(0)), C.c_void_p(out.data_ptr()), C.c_int64(out.stride(0)),
+                              C.c_int64(z.shape[0]), C.c_int64(z.shape[1]), C.c_void_p(_ptr(row_flags)),
+                              C.c_int32(flag_bit), stream_ptr()))
+
+
+def pack_weight_t(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> None:
+    """dst_bf16[c, r] = bf16(alpha * src_f32[r, c])."""
+    check(load().avc_pack_weight_t(C.c_void_p(src.data_ptr()), C.c_int64(src.stride(0)), C.c_void_p(dst.data_ptr()),
+                                   C.c_int64(dst.stride(0)), C.c_int64(src.shape[0]), C.c_int64(src.shape[1]),
+                                   C.c_float(alpha), stream_ptr()))

@@ -226,6 +226,13 @@ class ClipWhisperModel(nn.Module):
         llm_dtype = next(self.llm.parameters()).dtype  # clip_whisper_model.py:454
         table = self.llm.get_input_embeddings().weight
         pad_id = self.tokenizer.pad_token_id if self.tokenizer is not None else 0
+        if self.connector_type == "mlp":
+            return fused_connector(
+                a, v, None, None, None, None, self._plan(), input_ids=input_ids,
+                prompt_ids=self._prompt_ids(prompt), placeholder_id=placeholder_id, embed_table=table.detach(),
+                labels=labels, pad_id=pad_id, out_dtype=llm_dtype, audio_lengths=audio_lengths,
+                video_lengths=video_lengths, mlp_audio=self.audio_connector.mlp_params(),
+                mlp_video=self.video_connector.mlp_params())
         return fused_connector(
             a, v, self.audio_connector.linear.weight, self.audio_connector.linear.bias,
             self.video_connector.linear.weight, self.video_connector.linear.bias, self._plan(),

@@ -294,10 +294,12 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
                     input_ids: Optional[torch.Tensor] = None, prompt_ids: Optional[torch.Tensor] = None,
                     placeholder_id: int = -1, embed_table: Optional[torch.Tensor] = None,
                     labels: Optional[torch.Tensor] = None, pad_id: int = 0, out_dtype: torch.dtype = torch.bfloat16,
-                    audio_lengths=None, video_lengths=None, check: bool = False):
+                    audio_lengths=None, video_lengths=None, check: bool = False, mlp_audio=None, mlp_video=None):
     """Tower features -> (inputs_embeds [B, S, H], attention_mask int64 [B, S], labels int64 [B, S] | None).
 
     audio [B, Ta, Da] / video [B, Tv, Dv] (video may be a strided CLS view of CLIP's last_hidden_state).
+    mlp_audio / mlp_video = (fc1.weight, fc1.bias, fc2.weight, fc2.bias) select the two-layer GELU projector
+    instead of the linear one (wa, ba, wv, bv are then ignored).
     Layout: `input_ids` with `placeholder_id` runs marks where the AV tokens go; without it the reference layout
     `[prompt_ids[:, :32] | AV tokens]` is built (clip_whisper_model.py:448-451).
     audio_lengths / video_lengths (host ints or int32 tensors, valid frames per sample) switch to ragged packing:
@@ -357,8 +359,16 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
               placeholder_id=placeholder_id, pad_id=pad_id, embed_table=embed_table, labels=labels,
               uniform_layout=uniform_layout)
     dummy = torch.zeros(0, device=dev)
-    out = _FusedConnectorFn.apply(wa if use_a else dummy, ba if use_a else dummy, wv if use_v else dummy,
-                                  bv if use_v else dummy, st)
+    if mlp_audio is not None or mlp_video is not None:
+        # Linear -> GELU -> Linear per modality: (fc1.weight, fc1.bias, fc2.weight, fc2.bias)
+        from .mlp_ops import FusedMLPConnectorFn
+
+        pa = tuple(mlp_audio) if use_a else (dummy,) * 4
+        pv = tuple(mlp_video) if use_v else (dummy,) * 4
+        out = FusedMLPConnectorFn.apply(*pa, *pv, st)
+    else:
+        out = _FusedConnectorFn.apply(wa if use_a else dummy, ba if use_a else dummy, wv if use_v else dummy,
+                                      bv if use_v else dummy, st)
     if check and int(st["status"].item()) != 0:
         raise L.ConnectorError("placeholder count does not match the number of fused tokens for some sample")
     emb, mask = out[0], out[1]

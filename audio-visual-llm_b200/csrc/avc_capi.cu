@@ -425,6 +425,45 @@ int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_t batch,
   return AVC_OK;
 }
 
+static int run_gelu(const void* dh, int64_t dh_ld, const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows,
+                    int64_t cols, const uint8_t* row_flags, int32_t flag_bit, bool bwd, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (z == nullptr || out == nullptr || (bwd && dh == nullptr)) return fail(AVC_ERR_INVALID, "gelu: null pointer");
+  avc::GeluArgs g;
+  memset(&g, 0, sizeof(g));
+  g.z = static_cast<const uint8_t*>(z);
+  g.dh = static_cast<const uint8_t*>(dh);
+  g.out = static_cast<uint8_t*>(out);
+  g.rows = rows; g.cols = cols; g.z_ld = z_ld; g.dh_ld = dh_ld; g.out_ld = out_ld;
+  g.row_flags = row_flags;
+  g.flag_bit = flag_bit;
+  cudaError_t e = avc::launch_gelu(g, bwd, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, bwd ? "gelu_bwd launch" : "gelu_fwd launch");
+  return AVC_OK;
+}
+
+int avc_gelu_fwd(const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows, int64_t cols,
+                 const uint8_t* row_flags, int32_t flag_bit, void* stream) {
+  return run_gelu(nullptr, 0, z, z_ld, out, out_ld, rows, cols, row_flags, flag_bit, false, stream);
+}
+
+int avc_gelu_bwd(const void* dh, int64_t dh_ld, const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows,
+                 int64_t cols, const uint8_t* row_flags, int32_t flag_bit, void* stream) {
+  return run_gelu(dh, dh_ld, z, z_ld, out, out_ld, rows, cols, row_flags, flag_bit, true, stream);
+}
+
+int avc_pack_weight_t(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows, int64_t cols,
+                      float alpha, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (src == nullptr || dst_bf16 == nullptr) return fail(AVC_ERR_INVALID, "pack_weight_t: null pointer");
+  cudaError_t e = avc::launch_pack_weight_t(src, src_ld, dst_bf16, dst_ld, rows, cols, alpha,
+                                            static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "pack_weight_t launch");
+  return AVC_OK;
+}
+
 size_t avc_sumsq_workspace_bytes(void) { return avc::sumsq_workspace_bytes(); }
 
 int avc_sumsq(const float* x, int64_t n, float* out, void* workspace, int32_t accumulate, void* stream) {

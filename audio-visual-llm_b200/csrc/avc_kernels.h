@@ -148,6 +148,21 @@ struct ResampleArgs {
 };
 cudaError_t launch_row_resample(const ResampleArgs& args, cudaStream_t stream);
 
+// GELU (erf form, modality_connector.py:60) between the two layers of the MLP projector, with the per-row
+// "token present" mask of the fused connector:  fwd out = m * gelu(z);  bwd out = m * dh * gelu'(z).  bf16.
+struct GeluArgs {
+  const uint8_t* z;
+  const uint8_t* dh;   // bwd only
+  uint8_t* out;
+  int64_t rows, cols, z_ld, dh_ld, out_ld;  // leading dimensions in elements
+  const uint8_t* row_flags;  // [rows] or null (all rows on)
+  int flag_bit;              // mask applied to row_flags[r]
+};
+cudaError_t launch_gelu(const GeluArgs& args, bool backward, cudaStream_t stream);
+// dst_bf16[c, r] = bf16(alpha * src_f32[r, c])
+cudaError_t launch_pack_weight_t(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                                 int64_t cols, float alpha, cudaStream_t stream);
+
 // Trainer step for the projector parameters (clip_whisper_trainer.py:171-207, 453-464): deterministic
 // sum of squares of the gradient bucket (for the global-norm clip) and AdamW.
 size_t sumsq_workspace_bytes();

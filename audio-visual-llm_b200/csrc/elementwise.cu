@@ -169,6 +169,69 @@ __global__ void __launch_bounds__(128) row_resample_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------- MLP projector
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// FWD: out = mask(row) * gelu(z)            BWD: out = mask(row) * dh * gelu'(z)      (bf16, 8 elements per thread)
+template <bool BWD>
+__global__ void __launch_bounds__(256) gelu_kernel(const __grid_constant__ GeluArgs a) {
+  const int64_t vec_per_row = a.cols >> 3;
+  const int64_t total = a.rows * vec_per_row;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / vec_per_row;
+    const int64_t c = (g - r * vec_per_row) << 3;
+    const bool on = a.row_flags == nullptr || (__ldg(a.row_flags + r) & a.flag_bit) != 0;
+    int4 o = make_int4(0, 0, 0, 0);
+    if (on) {
+      const int4 zq = ld_nc_v4(a.z + (r * a.z_ld + c) * 2);
+      const uint32_t zw[4] = {static_cast<uint32_t>(zq.x), static_cast<uint32_t>(zq.y), static_cast<uint32_t>(zq.z),
+                              static_cast<uint32_t>(zq.w)};
+      uint32_t ow[4];
+      if (BWD) {
+        const int4 dq = ld_nc_v4(a.dh + (r * a.dh_ld + c) * 2);
+        const uint32_t dw[4] = {static_cast<uint32_t>(dq.x), static_cast<uint32_t>(dq.y),
+                                static_cast<uint32_t>(dq.z), static_cast<uint32_t>(dq.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          ow[e] = pack_bf16x2(bf_lo(dw[e]) * gelu_grad_f(bf_lo(zw[e])), bf_hi(dw[e]) * gelu_grad_f(bf_hi(zw[e])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ow[e] = pack_bf16x2(gelu_f(bf_lo(zw[e])), gelu_f(bf_hi(zw[e])));
+      }
+      o = make_int4(static_cast<int>(ow[0]), static_cast<int>(ow[1]), static_cast<int>(ow[2]), static_cast<int>(ow[3]));
+    }
+    st_na_v4(a.out + (r * a.out_ld + c) * 2, o);
+  }
+}
+
+// dst_bf16[c, r] = bf16(alpha * src_f32[r, c]): transposed weight pack for the input-gradient GEMM (dX = dY . W)
+__global__ void __launch_bounds__(256) pack_weight_t_kernel(const float* __restrict__ src, int64_t src_ld,
+                                                            uint8_t* __restrict__ dst, int64_t dst_ld, int64_t rows,
+                                                            int64_t cols, float alpha) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + r * src_ld + c) * alpha : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;  // output row = source column
+    if (c < cols && r < rows) {
+      const float x = tile[tx][i];
+      const uint32_t b = pack_bf16x2(x, 0.f);
+      reinterpret_cast<uint16_t*>(dst)[c * dst_ld + r] = static_cast<uint16_t>(b & 0xffffu);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- trainer step
 constexpr int SQ_BLOCKS = 592;  // 4 x 148
 constexpr int SQ_THREADS = 256;
@@ -252,6 +315,29 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Adam
 }
 
 }  // namespace
+
+cudaError_t launch_gelu(const GeluArgs& a, bool backward, cudaStream_t stream) {
+  if (a.rows <= 0 || a.cols <= 0) return cudaSuccess;
+  if (a.cols % 8 != 0 || a.z_ld % 8 != 0 || a.out_ld % 8 != 0 || (backward && a.dh_ld % 8 != 0) ||
+      (reinterpret_cast<uintptr_t>(a.z) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15) != 0 ||
+      (backward && (reinterpret_cast<uintptr_t>(a.dh) & 15) != 0))
+    return cudaErrorMisalignedAddress;
+  const int64_t total = a.rows * (a.cols >> 3);
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (backward) gelu_kernel<true><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  else gelu_kernel<false><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_weight_t(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                                 int64_t cols, float alpha, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  if (rows > 32 * 65535LL) return cudaErrorInvalidValue;
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  pack_weight_t_kernel<<<grid, 256, 0, stream>>>(src, src_ld, static_cast<uint8_t*>(dst), dst_ld, rows, cols, alpha);
+  return cudaGetLastError();
+}
 
 size_t sumsq_workspace_bytes() { return SQ_BLOCKS * sizeof(float); }
 

@@ -65,6 +65,39 @@ class SimpleModalityConnector(BaseModalityConnector):
         return linear_project(x, self.linear.weight, self.linear.bias, self.dtype)
 
 
+class MLPModalityConnector(BaseModalityConnector):
+    """Linear -> GELU(erf) -> Linear (LLaVA `mlp2x_gelu`); new on this path (north_star "linear/MLP projector").
+    Parameters: fc1.weight [hidden_dim, input_dim], fc1.bias, fc2.weight [output_dim, hidden_dim], fc2.bias."""
+
+    def __init__(self, input_dim, output_dim, device="cuda", dtype=torch.float32, max_seq_len=None, hidden_dim=None,
+                 **kwargs):
+        super().__init__(input_dim, output_dim, device, dtype)
+        hidden_dim = hidden_dim or output_dim
+        if input_dim % 8 or output_dim % 8 or hidden_dim % 8:
+            raise ValueError("input_dim, hidden_dim and output_dim must be multiples of 8")
+        self.hidden_dim = hidden_dim
+        self.fc1 = nn.Linear(input_dim, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, output_dim)
+        for lin in (self.fc1, self.fc2):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+        self.fc1 = self.fc1.to(device=device, dtype=torch.float32)
+        self.fc2 = self.fc2.to(device=device, dtype=torch.float32)
+
+    def mlp_params(self):
+        return (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+
+    def _forward_impl(self, x):
+        from .connector_ops import FusePlan, fused_connector
+
+        squeeze = x.dim() == 2
+        if squeeze:
+            x = x.unsqueeze(0)
+        emb, _, _ = fused_connector(x, None, None, None, None, None, FusePlan(modality="audio"),
+                                    out_dtype=self.dtype, mlp_audio=self.mlp_params())
+        return emb[0] if squeeze else emb
+
+
 class UnsupportedConnector(BaseModalityConnector):
     def __init__(self, *args, **kwargs):
         raise NotImplementedError(
@@ -75,10 +108,10 @@ class UnsupportedConnector(BaseModalityConnector):
 
 def create_modality_connector(connector_type, input_dim, output_dim, **kwargs):
     """Factory with the reference's signature (modality_connector.py:383-399)."""
-    connector_map = {"simple": SimpleModalityConnector}
+    connector_map = {"simple": SimpleModalityConnector, "mlp": MLPModalityConnector}
     if connector_type not in connector_map:
         raise NotImplementedError(
-            f"connector type {connector_type!r} is not available on the B200 path (only 'simple'); the reference "
+            f"connector type {connector_type!r} is not available on the B200 path ('simple' or 'mlp'); the reference "
             "would fall back to 'deep' here and then fail with a TypeError (SURVEY.md 8(a) A2)")
     return connector_map[connector_type](input_dim, output_dim, **kwargs)
 

@@ -156,6 +156,19 @@ AVC_API int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_
                              int32_t dst_rows, int32_t hidden, const int32_t* row_ptr, const int32_t* col_idx,
                              const float* weight, void* stream);
 
+/* ---- MLP projector helpers (Linear -> GELU -> Linear; north_star extension, erf GELU as modality_connector.py:60)
+ * avc_gelu_fwd:  out[r, :] = flag(r) ? gelu(z[r, :]) : 0          avc_gelu_bwd: out[r, :] = flag(r) ? dh * gelu'(z) : 0
+ *   bf16 matrices (rows x cols, leading dimensions in elements); flag(r) = row_flags[r] & flag_bit (all on if NULL).
+ *   Forward-only inference can use the GELU epilogue of avc_proj_fwd (act = 1) instead.
+ * avc_pack_weight_t: dst_bf16[c, r] = bf16(alpha * src_f32[r, c]) -- the transposed operand of the input-gradient
+ *   GEMM  dX = dY . W  (avc_proj_fwd with A = dY, W = this). */
+AVC_API int avc_gelu_fwd(const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows, int64_t cols,
+                         const uint8_t* row_flags, int32_t flag_bit, void* stream);
+AVC_API int avc_gelu_bwd(const void* dh, int64_t dh_ld, const void* z, int64_t z_ld, void* out, int64_t out_ld,
+                         int64_t rows, int64_t cols, const uint8_t* row_flags, int32_t flag_bit, void* stream);
+AVC_API int avc_pack_weight_t(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows,
+                              int64_t cols, float alpha, void* stream);
+
 /* ---- trainer step for the projector parameters ----------------------------------------------------
  * Replaces, for the connector parameters, clip_grad_norm_ + AdamW.step of the reference trainer
  * (clip_whisper_trainer.py:171-207 param groups / AdamW(betas=(0.9, 0.95), eps=1e-8), :453-464 step).

@@ -262,3 +262,29 @@ def connector_grads(audio_feats, video_feats, wa, ba, wv, bv, spec: ConnectorSpe
     tokens, _ = connector_tokens(audio_feats, video_feats, *params, spec)
     (tokens * upstream_tokens.to(tokens.dtype)).sum().backward()
     return [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+
+
+def connector_tokens_mlp(audio_feats, video_feats, mlp_a, mlp_v, spec: ConnectorSpec, audio_valid=None,
+                         video_valid=None):
+    """Two-layer GELU projector per modality (new; LLaVA mlp2x_gelu with the erf GELU of modality_connector.py:60):
+    tokens = sum_s scale_s * present_s * (gelu(x_s W1_s^T + b1_s) W2_s^T + b2_s), stacking / presence as
+    connector_tokens().  mlp_* = (fc1.weight, fc1.bias, fc2.weight, fc2.bias)."""
+    use_a = spec.modality in ("audio", "both") and audio_feats is not None
+    use_v = spec.modality in ("video", "both") and video_feats is not None
+    N = token_counts(spec, audio_feats.shape[1] if use_a else None, video_feats.shape[1] if use_v else None)
+    sa, sv = (spec.fusion_scale, 1 - spec.fusion_scale) if (use_a and use_v and spec.fusion == "sum") else (1.0, 1.0)
+    B = (audio_feats if use_a else video_feats).shape[0]
+    j = torch.arange(N).unsqueeze(0)
+    out = None
+    for use, x, p, k, valid, s in [(use_a, audio_feats, mlp_a, spec.audio_stride, audio_valid, sa),
+                                   (use_v, video_feats, mlp_v, spec.video_stride, video_valid, sv)]:
+        if not use:
+            continue
+        w1, b1, w2, b2 = p
+        T = x.shape[1]
+        n_valid = torch.full((B,), T) if valid is None else valid.clamp(0, T).to(torch.long)
+        present = ((j * k) < n_valid.unsqueeze(1)).unsqueeze(-1).to(w1.dtype)
+        h = F.gelu(stack_frames(x.to(w1.dtype), k, N, valid) @ w1.t() + b1)
+        y = s * present * (h @ w2.t() + b2)
+        out = y if out is None else out + y
+    return out

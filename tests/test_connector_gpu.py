@@ -321,3 +321,105 @@ def test_step_engine_fused_equals_unfused_and_oracle(avc, cuda_dev, modality, ka
     for n, gr in zip(names, grads):
         if n in g1:
             assert_close(g1[n], gr, n)
+
+
+def _mlp_params(g, Hd, K, H):
+    return [torch.randn(Hd, K, generator=g) / K ** 0.5, torch.randn(Hd, generator=g) * 0.1,
+            torch.randn(H, Hd, generator=g) / Hd ** 0.5, torch.randn(H, generator=g) * 0.1]
+
+
+@pytest.mark.parametrize("case", ["direct_concat", "padded_sum", "ragged_video"])
+def test_mlp_projector_fwd_bwd_vs_oracle(avc, cuda_dev, case):
+    """Linear -> GELU -> Linear projector through the fused connector: forward and all eight parameter gradients."""
+    g = torch.Generator().manual_seed(61)
+    B, Da, Dv, Hd, H, P, V = 2, 32, 16, 96, 64, 3, 30
+    dev = cuda_dev
+    kwargs = {}
+    if case == "direct_concat":  # both streams dense, stride 4 / 2 -> free views, no gather
+        Ta, Tv, ka, kv, fusion = 40, 20, 4, 2, "concat"
+        a, v = torch.randn(B, Ta, Da, generator=g), torch.randn(B, Tv, Dv, generator=g)
+        av = vv = None
+    elif case == "padded_sum":   # reference-style: k=1, video shorter -> padded rows must get no video output at all
+        Ta, Tv, ka, kv, fusion = 24, 9, 1, 1, "sum"
+        a, v = torch.randn(B, Ta, Da, generator=g), torch.randn(B, Tv, Dv, generator=g)
+        av = vv = None
+    else:
+        Ta, Tv, ka, kv, fusion = 8, 20, 1, 1, "sum"
+        a, v = None, torch.randn(B, Tv, Dv, generator=g)
+        av, vv = None, torch.tensor([20, 7])
+    pa, pv = _mlp_params(g, Hd, ka * Da, H), _mlp_params(g, Hd, kv * Dv, H)
+    modality = "video" if a is None else "both"
+    spec = O.ConnectorSpec(modality=modality, fusion=fusion, fusion_scale=0.3, audio_stride=ka, video_stride=kv,
+                           max_seq_len=64, mask_mode=1 if vv is not None else 0)
+    pa_c = [t.clone().requires_grad_(True) for t in pa]
+    pv_c = [t.clone().requires_grad_(True) for t in pv]
+    tok = O.connector_tokens_mlp(a, v, pa_c, pv_c, spec, video_valid=vv)
+    N = tok.shape[1]
+    table = torch.randn(V, H, generator=g)
+    if vv is None:
+        prompt = torch.randint(1, V - 1, (B, P), generator=g)
+        ids = torch.cat([prompt, torch.full((B, N), V - 1)], 1)
+        ntok = None
+    else:
+        lens = vv.tolist()
+        ids = torch.zeros(B, P + N, dtype=torch.int64)
+        for b, n in enumerate(lens):
+            row = torch.randint(1, V - 1, (P + N,), generator=g)
+            row[1:1 + n] = V - 1
+            row[1 + n + 2:] = 0
+            ids[b] = row
+        ntok = vv
+    emb_r, mask_r, _ = O.splice_tokens(tok, ids, V - 1, table, 0, spec, ntok=ntok)
+    up = torch.randn(emb_r.shape, generator=g)
+    (emb_r * up).sum().backward()
+    pa_d = [t.to(dev).requires_grad_(True) for t in pa]
+    pv_d = [t.to(dev).requires_grad_(True) for t in pv]
+    plan = avc.FusePlan(modality=modality, fusion=fusion, fusion_scale=0.3, audio_stride=ka, video_stride=kv,
+                        max_seq_len=64, mask_mode=1 if vv is not None else 0)
+    common = dict(embed_table=table.to(dev, torch.bfloat16), out_dtype=torch.bfloat16, check=True,
+                  mlp_audio=pa_d if a is not None else None, mlp_video=pv_d)
+    if vv is None:
+        emb, mask, _ = avc.fused_connector(a.to(dev), v.to(dev), None, None, None, None, plan,
+                                           prompt_ids=ids[:, :P].to(dev), placeholder_id=V - 1, **common)
+    else:
+        emb, mask, _ = avc.fused_connector(None, v.to(dev), None, None, None, None, plan, input_ids=ids.to(dev),
+                                           placeholder_id=V - 1, video_lengths=vv.tolist(), **common)
+    (emb.float() * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    is_ph = ids == V - 1
+    assert_close(emb[is_ph.to(dev)], emb_r[is_ph], "AV rows")
+    assert torch.equal(emb.cpu()[~is_ph], emb_r[~is_ph].to(torch.bfloat16))
+    assert torch.equal(mask.cpu(), mask_r)
+    names = ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    for tag, dev_p, cpu_p in (("audio", pa_d, pa_c), ("video", pv_d, pv_c)):
+        if tag == "audio" and a is None:
+            continue
+        for n, pd, pc in zip(names, dev_p, cpu_p):
+            assert_close(pd.grad, pc.grad, f"{tag}.{n}")
+    # forward-only (no grad): GELU runs in the GEMM epilogue when every token is present
+    with torch.no_grad():
+        if vv is None:
+            emb2, _, _ = avc.fused_connector(a.to(dev), v.to(dev), None, None, None, None, plan,
+                                             prompt_ids=ids[:, :P].to(dev), placeholder_id=V - 1, **common)
+            assert_close(emb2[is_ph.to(dev)], emb_r[is_ph], "AV rows (epilogue GELU)")
+
+
+def test_mlp_modality_connector_module(avc, cuda_dev):
+    g = torch.Generator().manual_seed(62)
+    conn = avc.create_modality_connector("mlp", 64, 96, device="cuda:0", hidden_dim=128)
+    assert set(conn.state_dict()) == {"fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"}
+    with torch.no_grad():
+        conn.fc1.bias.copy_(torch.randn(128, generator=g) * 0.1)
+        conn.fc2.bias.copy_(torch.randn(96, generator=g) * 0.1)
+    x = torch.randn(3, 40, 64, generator=g)
+    p = [t.detach().cpu().clone().requires_grad_(True) for t in conn.mlp_params()]
+    ref = torch.nn.functional.gelu(x @ p[0].t() + p[1]) @ p[2].t() + p[3]
+    up = torch.randn(ref.shape, generator=g)
+    (ref * up).sum().backward()
+    y = conn(x.to(cuda_dev))
+    (y * up.to(cuda_dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float32
+    assert_close(y, ref, "y")
+    for t, r, n in zip(conn.mlp_params(), p, ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]):
+        assert_close(t.grad, r.grad, n)
