@@ -146,11 +146,11 @@ def proj_fwd(a_segs: Sequence[torch.Tensor], w_segs: Sequence[torch.Tensor], y: 
 
 
 def proj_bwd_dw(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
-                alpha: Sequence[float], dy_row_base: int = 0) -> None:
+                alpha: Sequence[float], dy_row_base: int = 0, max_sms: int = 0) -> None:
     al = (C.c_float * len(x_segs))(*alpha)
     check(load().avc_proj_bwd_dw(
         C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
-        _mat_array([mat(t) for t in dw_segs]), al, stream_ptr()))
+        _mat_array([mat(t) for t in dw_segs]), al, C.c_int32(max_sms), stream_ptr()))
 
 
 def colsum_workspace(cols: int, device) -> torch.Tensor:

@@ -248,9 +248,11 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
 }
 
 int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
-                    const float* alpha, void* stream) {
+                    const float* alpha, int32_t max_sms, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
+  if (max_sms < 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: negative max_sms");
+  if (max_sms >= 2 && max_sms < di.num_sms) di.num_sms = max_sms & ~1;  // whole CTA pairs
   if (nseg < 1 || nseg > 2) return fail(AVC_ERR_INVALID, "proj_bwd_dw: nseg must be 1 or 2");
   if (dy == nullptr || x == nullptr || dw == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw: null matrix");
   const int64_t H = dy->cols;

@@ -118,6 +118,10 @@ class ConnectorStep:
         npack = int(self.use_a) + int(self.use_v)
         self.launches_per_step = npack + (3 if self.direct else 5) + 2  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum x2
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
+        self.overlap_comm = True       # N > 1: all-reduce finished gradients while the rest is computed
+        self.comm_reserve_sms = 16     # SMs the second dW launch leaves to the concurrent NCCL kernel
+        self._comm_stream = None
+        self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     # ------------------------------------------------------------------ algorithmic work per step
     @property
@@ -134,7 +138,8 @@ class ConnectorStep:
         return 2 * self.M * self.shape.hidden * 2 + 16 * self.shape.batch * self.S
 
     # ------------------------------------------------------------------ the step
-    def enable_kernel_timing(self, names=("gather", "proj_fwd", "splice_fwd", "splice_bwd", "proj_bwd_dw", "colsum")):
+    def enable_kernel_timing(self, names=("gather", "proj_fwd", "splice_fwd", "splice_bwd", "proj_bwd_dw",
+                                          "proj_bwd_dw_v", "colsum")):
         self.events = {n: [] for n in names}
 
     def _timed(self, name, fn):
@@ -181,27 +186,56 @@ class ConnectorStep:
     def backward(self, allreduce: bool = True):
         g = self.bucket
         B, N, P = self.shape.batch, self.N, self.shape.prompt_len
-        dws, al = [], []
-        if self.use_a:
-            dws.append(g["audio_connector.linear.weight"]); al.append(self.sa)
-        if self.use_v:
-            dws.append(g["video_connector.linear.weight"]); al.append(self.sv)
         dba = g["audio_connector.linear.bias"] if self.use_a else None
         dbv = g["video_connector.linear.bias"] if self.use_v else None
         if self.direct:
-            xs = ([self.audio.view(B, N, self.Ka)] if self.use_a else []) + \
-                 ([self.video.view(B, N, self.Kv)] if self.use_v else [])
-            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(self.d_emb, xs, dws, al, dy_row_base=P))
-            self._timed("colsum", lambda: L.colsum(self.d_emb, dba, dbv, self.colsum_ws, alpha0=self.sa,
-                                                   alpha1=self.sv, dy_row_base=P, sum_rows=N))
+            dy, base = self.d_emb, P
+            xa = self.audio.view(B, N, self.Ka) if self.use_a else None
+            xv = self.video.view(B, N, self.Kv) if self.use_v else None
+            cs = dict(dy_row_base=P, sum_rows=N)
         else:
             self._timed("splice_bwd", lambda: L.splice_bwd(self.sp, self.d_emb, self.dY))
-            xs = ([self.A[:, :self.Ka]] if self.use_a else []) + ([self.A[:, self.Ka:]] if self.use_v else [])
-            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(self.dY, xs, dws, al))
-            self._timed("colsum", lambda: L.colsum(self.dY, dba, dbv, self.colsum_ws, row_flags=self.flags,
-                                                   alpha0=self.sa, alpha1=self.sv))
-        if allreduce:
-            g.allreduce()
+            dy, base = self.dY, 0
+            xa = self.A[:, :self.Ka] if self.use_a else None
+            xv = self.A[:, self.Ka:] if self.use_v else None
+            cs = dict(row_flags=self.flags)
+        overlap = allreduce and self.overlap_comm and g.world_size() > 1 and self.use_a and self.use_v
+        if not overlap:
+            xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
+            dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
+                  ([g["video_connector.linear.weight"]] if self.use_v else [])
+            al = ([self.sa] if self.use_a else []) + ([self.sv] if self.use_v else [])
+            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, xs, dws, al, dy_row_base=base))
+            self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv, **cs))
+            if allreduce:
+                g.allreduce()
+            return g
+        # Data-parallel overlap: the audio weight gradient (2/3 of the bucket at cfg2) is all-reduced on a side stream
+        # while the video weight gradient and the bias sums are still being computed on `comm_reserve_sms` fewer SMs;
+        # the rest of the bucket follows.  Same arithmetic, same results as the single all-reduce.
+        main = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        comm = self._comm_stream
+        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, [xa], [g["audio_connector.linear.weight"]], [self.sa],
+                                                         dy_row_base=base))
+        e1 = torch.cuda.Event()
+        e1.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(e1)
+            g.allreduce_span("audio_connector.linear.weight", "audio_connector.linear.weight")
+        sms = self._num_sms - self.comm_reserve_sms
+        self._timed("proj_bwd_dw_v", lambda: L.proj_bwd_dw(dy, [xv], [g["video_connector.linear.weight"]], [self.sv],
+                                                           dy_row_base=base, max_sms=sms))
+        self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv, **cs))
+        e2 = torch.cuda.Event()
+        e2.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(e2)
+            g.allreduce_span("video_connector.linear.weight", "video_connector.linear.bias")
+            e3 = torch.cuda.Event()
+            e3.record(comm)
+        main.wait_event(e3)
         return g
 
     def step(self, allreduce: bool = True):

@@ -62,6 +62,27 @@ class GradBucket:
         self.flat.div_(ws)
         return work
 
+    def span(self, first: str, last: str) -> torch.Tensor:
+        """Contiguous slice of the flat buffer covering views `first` .. `last` (in bucket order)."""
+        names = list(self.views)
+        i, j = names.index(first), names.index(last)
+        lo = self.views[names[i]].data_ptr() - self.flat.data_ptr()
+        hi = self.views[names[j]].data_ptr() - self.flat.data_ptr() + self.views[names[j]].numel() * 4
+        return self.flat[lo // 4: hi // 4]
+
+    def allreduce_span(self, first: str, last: str):
+        """Average only views `first` .. `last`; used to overlap the reduction of finished gradients with the
+        kernels that still produce the rest."""
+        ws = self.world_size()
+        if ws == 1:
+            return
+        t = self.span(first, last)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(ws)
+
     def attach(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]]) -> None:
         """Point each parameter's .grad at its bucket view (so optimizers / clip_grad_norm_ see the reduced grads)."""
         for name, p in named_params:

@@ -95,7 +95,8 @@ AVC_API int avc_proj_fwd(int32_t nseg, const avc_mat* a /* [nseg] bf16 */, const
  * clip_whisper_model.py:1096,1136). */
 AVC_API int avc_proj_bwd_dw(const avc_mat* dy /* bf16 [b][rows][H] */, int32_t dy_row_base, int32_t nseg,
                     const avc_mat* x /* [nseg] bf16 */, const avc_mat* dw /* [nseg] fp32 [H, K_s] */,
-                    const float* alpha /* [nseg] */, void* stream);
+                    const float* alpha /* [nseg] */, int32_t max_sms /* 0 = all; < SM count leaves SMs free for a
+                    concurrent collective (gradient all-reduce overlap) */, void* stream);
 
 /* ---- bias gradient: deterministic two-pass column sum over flagged rows -------------------------
  * out_i[c] = alpha_i * sum_{b, r < sum_rows : flag_i(b, r)} dY[b, dy_row_base + r, c]      (db = sum dY)
