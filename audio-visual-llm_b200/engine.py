@@ -12,6 +12,7 @@ single NCCL call.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -119,7 +120,8 @@ class ConnectorStep:
         self.launches_per_step = npack + (3 if self.direct else 5) + 2  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum x2
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
         self.overlap_comm = True       # N > 1: all-reduce finished gradients while the rest is computed
-        self.comm_reserve_sms = 16     # SMs the second dW launch leaves to the concurrent NCCL kernel
+        # SMs the second dW launch leaves to the concurrent NCCL kernel
+        self.comm_reserve_sms = int(os.environ.get("AVC_COMM_RESERVE_SMS", "16"))
         self._comm_stream = None
         self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 

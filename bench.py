@@ -149,7 +149,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if "AVC_KEEP_NCCL_DEBUG" not in os.environ:
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)  # NCCL / c10d print a version banner on stdout when the communicator is created
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     peaks = load_peaks()
     w = WORKLOAD
     plan = pkg.FusePlan(modality=w["modality"], fusion=w["fusion"], fusion_scale=w["fusion_scale"],
