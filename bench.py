@@ -100,7 +100,7 @@ def reference_arm(args, rank: int):
         return
     from oracle import cpu_baseline
 
-    sample_batch = 4
+    sample_batch = 8
     tok_s, dt, threads = cpu_baseline.time_cpu(WORKLOAD, sample_batch, args.steps, args.warmup)
     sample = (f"batch {sample_batch} of {WORKLOAD['batch_per_gpu']} (same shapes) per step, fp32 torch CPU, "
               f"{args.warmup} warm-up + {args.steps} timed fwd+bwd steps")
