@@ -112,3 +112,38 @@ def test_reference_arm_and_cpu_baseline_run(avc):
     assert tok_s > 0 and threads >= 1
     emb, mask, lab, grads = cpu_baseline.one_step(cpu_baseline.make_case(wl, 2))
     assert emb.shape == (2, 14, 32) and mask.dtype == torch.int64 and grads[0].shape == (32, 64)
+
+
+def test_config_keys_follow_the_reference_yaml(avc, tmp_path):
+    """The shipped reference yaml layout (nested model:/data:) loads; new keys default to reference behaviour."""
+    from audio_visual_llm_b200.config import load_config, model_kwargs
+
+    ref_yaml = """
+data:
+  max_seq_len: 512
+model:
+  llm_path: "checkpoints/Llama-3.2-1B"
+  whisper_model: "openai/whisper-medium"
+  modality: "both"
+  use_fp16: false
+  freeze_encoders: true
+  fusion_scale: 0.5
+"""
+    p = tmp_path / "clip_whisper.yaml"
+    p.write_text(ref_yaml)
+    kw = load_config(str(p))
+    assert kw["max_seq_len"] == 512 and kw["modality"] == "both" and kw["fusion_scale"] == 0.5
+    assert kw["llm_path"] == "checkpoints/Llama-3.2-1B" and kw["connector_type"] == "simple"
+    assert (kw["fusion"], kw["stride"], kw["align"], kw["mask_mode"], kw["label_mode"]) == ("sum", 1, "index", 0, 0)
+    kw = model_kwargs({"model": {"fusion": "concat", "stride": 4, "align": "rate"}, "modality": "audio"})
+    assert kw["fusion"] == "concat" and kw["stride"] == 4 and kw["align"] == "rate" and kw["modality"] == "audio"
+    with pytest.raises(ValueError):
+        model_kwargs({"model": {"fusion": "attention"}})
+
+
+def test_optimizer_decay_groups_follow_the_reference(avc):
+    """'bias' in the parameter name -> no weight decay (clip_whisper_trainer.py:188)."""
+    from audio_visual_llm_b200.trainer_step import ConnectorAdamW
+
+    assert ConnectorAdamW.decay_for(type("X", (), {"weight_decay": 0.01})(), "audio_connector.linear.bias") == 0.0
+    assert ConnectorAdamW.decay_for(type("X", (), {"weight_decay": 0.01})(), "video_connector.linear.weight") == 0.01

@@ -106,6 +106,12 @@ def main():
     report("splice_fwd", lambda: L.splice_fwd(sp, Y, emb), nbytes=2 * B * S * H * 2 + 16 * B * S)
     report("splice_bwd", lambda: L.splice_bwd(sp, d_emb, dY), nbytes=2 * M * H * 2)
     report("proj_bwd_dw", lambda: L.proj_bwd_dw(dY, [A], [dW], [1.0]), flops=2 * M * K * H)
+    # same FLOPs / tile grid as the dW GEMM, but K-major operands (TN mode): isolates the cost of the MN-major path
+    At = torch.randn(H, M, device=dev).to(torch.bfloat16)
+    Wt = torch.randn(K, M, device=dev).to(torch.bfloat16)
+    Yt = torch.empty(H, K, dtype=torch.float32, device=dev)
+    report("tn_gemm_dw_shape_f32out", lambda: L.proj_fwd([At], [Wt], Yt), flops=2 * M * K * H)
+    del At, Wt, Yt
     report("colsum", lambda: L.colsum(dY, db, None, ws), nbytes=M * H * 2)
     report("torch_matmul_fwd", lambda: torch.matmul(A, W.t(), out=Y), flops=2 * M * K * H)
     dWb = torch.empty(H, K, dtype=torch.bfloat16, device=dev)
