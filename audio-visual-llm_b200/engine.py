@@ -123,6 +123,10 @@ class ConnectorStep:
         # SMs the second dW launch leaves to the concurrent NCCL kernel
         self.comm_reserve_sms = int(os.environ.get("AVC_COMM_RESERVE_SMS", "16"))
         self._comm_stream = None
+        self._side_stream = None
+        # run the small HBM-bound kernels of the fused step (text rows + masks, bias sums) on a side stream,
+        # concurrently with the GEMMs
+        self.side_streams = os.environ.get("AVC_SIDE_STREAMS", "1") != "0"
         self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     # ------------------------------------------------------------------ algorithmic work per step
@@ -154,6 +158,23 @@ class ConnectorStep:
         e.record()
         self.events[name].append((s, e))
 
+    def _on_side(self, name, fn):
+        """Run a small HBM-bound kernel on the side stream, concurrently with the tensor-bound GEMM that follows on
+        the main stream (the GEMM's CTAs leave threads, registers and HBM bandwidth free on every SM).  Returns the
+        event the main stream must wait for before anything consumes the kernel's output."""
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fork)
+            self._timed(name, fn)
+            done = torch.cuda.Event()
+            done.record(side)
+        return done
+
     def forward(self):
         p = self.plan
         col = 0
@@ -175,9 +196,14 @@ class ConnectorStep:
             xs = ([self.audio.view(self.M, self.Ka)] if self.use_a else []) + \
                  ([self.video.view(self.M, self.Kv)] if self.use_v else [])
             wsegs = ([self.wp[:, :self.Ka]] if self.use_a else []) + ([self.wp[:, self.Ka:]] if self.use_v else [])
+            if self.side_streams:
+                done = self._on_side("splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
             self._timed("proj_fwd", lambda: L.proj_fwd(xs, wsegs, self.emb_av, bias0=b0, bias1=b1, bias_scale0=s0,
                                                        bias_scale1=s1))
-            self._timed("splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
+            if self.side_streams:
+                torch.cuda.current_stream().wait_event(done)
+            else:
+                self._timed("splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
             return self.emb, self.mask, self.labels_out
         else:
             self._timed("proj_fwd", lambda: L.proj_fwd([self.A], [self.wp], self.Y, bias0=b0, bias1=b1,
@@ -202,13 +228,22 @@ class ConnectorStep:
             xv = self.A[:, self.Ka:] if self.use_v else None
             cs = dict(row_flags=self.flags)
         overlap = allreduce and self.overlap_comm and g.world_size() > 1 and self.use_a and self.use_v
+        cs_done = None
+        if self.side_streams and self.direct:
+            # the bias column sums only read d(inputs_embeds): run them under the dW GEMM
+            cs_done = self._on_side("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa,
+                                                               alpha1=self.sv, **cs))
         if not overlap:
             xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
             dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
                   ([g["video_connector.linear.weight"]] if self.use_v else [])
             al = ([self.sa] if self.use_a else []) + ([self.sv] if self.use_v else [])
             self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, xs, dws, al, dy_row_base=base))
-            self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv, **cs))
+            if cs_done is not None:
+                torch.cuda.current_stream().wait_event(cs_done)
+            else:
+                self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv,
+                                                       **cs))
             if allreduce:
                 g.allreduce()
             return g
@@ -229,7 +264,10 @@ class ConnectorStep:
         sms = self._num_sms - self.comm_reserve_sms
         self._timed("proj_bwd_dw_v", lambda: L.proj_bwd_dw(dy, [xv], [g["video_connector.linear.weight"]], [self.sv],
                                                            dy_row_base=base, max_sms=sms))
-        self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv, **cs))
+        if cs_done is not None:
+            main.wait_event(cs_done)
+        else:
+            self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv, **cs))
         e2 = torch.cuda.Event()
         e2.record(main)
         with torch.cuda.stream(comm):
