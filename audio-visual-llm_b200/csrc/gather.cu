@@ -17,8 +17,8 @@ namespace avc {
 namespace {
 
 constexpr int G_WARPS = 4;
-constexpr int G_STAGES = 4;
-constexpr int G_LOOKAHEAD = 2;  // loads in flight per warp; stage reuse distance = G_STAGES - 2 stores
+constexpr int G_STAGES = 6;
+constexpr int G_LOOKAHEAD = 4;  // loads in flight per warp; stage reuse distance = G_STAGES - G_LOOKAHEAD stores
 
 struct Item {
   const uint8_t* src;
@@ -125,27 +125,41 @@ __global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_const
       }
     };
 
-    // loads run G_LOOKAHEAD items ahead of stores
-    for (int64_t n = 0; n < G_LOOKAHEAD && n < my_items; ++n) issue_load(make_item(n), n);
+    // loads run G_LOOKAHEAD items ahead of stores; the items in flight are kept in registers
+    Item ring[G_LOOKAHEAD];
+#pragma unroll
+    for (int i = 0; i < G_LOOKAHEAD; ++i) {
+      if (i < my_items) {
+        ring[i] = make_item(i);
+        issue_load(ring[i], i);
+      }
+    }
     uint32_t phase_bits = 0;  // bit s = parity of the next load phase to wait for on stage s
-    for (int64_t n = 0; n < my_items; ++n) {
-      const int64_t na = n + G_LOOKAHEAD;
-      if (na < my_items) {
-        // stage (na % G_STAGES) was last read by the store of item na - G_STAGES = n - 2
-        bulk_wait_read<G_STAGES - G_LOOKAHEAD - 1>();
-        issue_load(make_item(na), na);
+    for (int64_t n0 = 0; n0 < my_items; n0 += G_LOOKAHEAD) {
+#pragma unroll
+      for (int i = 0; i < G_LOOKAHEAD; ++i) {
+        const int64_t n = n0 + i;
+        if (n >= my_items) break;
+        const Item it = ring[i];
+        const int s = static_cast<int>(n % G_STAGES);
+        const int fb = a.frame_bytes[it.mod];
+        if (it.nvalid > 0) {
+          mbar_wait(s_bar + 8 * s, (phase_bits >> s) & 1u);
+          phase_bits ^= 1u << s;
+          bulk_s2g(it.dst, s_ring + s * stage_bytes, static_cast<uint32_t>(it.nvalid * fb));
+        }
+        for (int f = 0; f < it.nzero; ++f)
+          bulk_s2g(it.dst + static_cast<int64_t>(it.nvalid + f) * fb, s_zero, fb);
+        bulk_commit();
+        const int64_t na = n + G_LOOKAHEAD;
+        if (na < my_items) {
+          // stage (na % G_STAGES) was last read by the store group of item na - G_STAGES = n - (G_STAGES -
+          // G_LOOKAHEAD); the G_STAGES - G_LOOKAHEAD groups committed after it may still be reading their stages
+          bulk_wait_read<G_STAGES - G_LOOKAHEAD>();
+          ring[i] = make_item(na);
+          issue_load(ring[i], na);
+        }
       }
-      const Item it = make_item(n);
-      const int s = static_cast<int>(n % G_STAGES);
-      const int fb = a.frame_bytes[it.mod];
-      if (it.nvalid > 0) {
-        mbar_wait(s_bar + 8 * s, (phase_bits >> s) & 1u);
-        phase_bits ^= 1u << s;
-        bulk_s2g(it.dst, s_ring + s * stage_bytes, static_cast<uint32_t>(it.nvalid * fb));
-      }
-      for (int f = 0; f < it.nzero; ++f)
-        bulk_s2g(it.dst + static_cast<int64_t>(it.nvalid + f) * fb, s_zero, fb);
-      bulk_commit();
     }
     bulk_wait_all<0>();
   }

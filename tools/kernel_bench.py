@@ -99,6 +99,12 @@ def main():
         print(json.dumps(rec), flush=True)
 
     report("gather", lambda: L.gather_fwd(audio, video, ka, kv, B, N, A, flags), nbytes=2 * M * K * 2)
+    # reference-parity shapes: k = 1, video zero-padded from 750 to 1500 tokens (cfg2')
+    A1 = torch.empty(B * Ta, Da + Dv, dtype=torch.bfloat16, device=dev)
+    f1 = torch.empty(B * Ta, dtype=torch.uint8, device=dev)
+    report("gather_k1_parity", lambda: L.gather_fwd(audio, video, 1, 1, B, Ta, A1, f1),
+           nbytes=(B * Ta * Da + B * Tv * Dv) * 2 + B * Ta * (Da + Dv) * 2)
+    del A1, f1
     report("proj_fwd", lambda: L.proj_fwd([A], [W], Y, bias0=bias), flops=2 * M * K * H)
     report("proj_fwd_2seg", lambda: L.proj_fwd([A[:, :ka * Da], A[:, ka * Da:]], [W[:, :ka * Da], W[:, ka * Da:]], Y,
                                                bias0=bias, bias1=bias, row_flags=flags), flops=2 * M * K * H)
