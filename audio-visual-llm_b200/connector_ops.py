@@ -88,8 +88,23 @@ def to_bf16_features(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float]) -> torch.Tensor:
-    """[H, K_s] fp32 master weights -> one bf16 [H, sum K_s] matrix with the fusion scales folded in."""
+_PACK_CACHE: dict = {}
+_PACK_CACHE_MAX = 16
+
+
+def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float], cache: bool = False) -> torch.Tensor:
+    """[H, K_s] fp32 master weights -> one bf16 [H, sum K_s] matrix with the fusion scales folded in.
+
+    Forward-only calls (`cache=True`: no gradient is recorded for the weights -- decode / generate,
+    clip_whisper_model.py:1301-1340) reuse the packed
+    copy while the parameters are unchanged (same storage and torch version counter), so a latency-bound encode is
+    GEMM + splice only.  Training re-packs every step: the optimizer has changed the weights."""
+    key = None
+    if cache:  # the caller is not recording gradients for these weights
+        key = tuple((w.data_ptr(), w._version, tuple(w.shape), float(s)) for w, s in zip(weights, scales))
+        hit = _PACK_CACHE.get(key)
+        if hit is not None:
+            return hit
     H = weights[0].shape[0]
     K = sum(w.shape[1] for w in weights)
     packed = torch.empty(H, K, dtype=torch.bfloat16, device=weights[0].device)
@@ -99,6 +114,10 @@ def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float]) -> 
             raise ValueError("projector master weights must be fp32 with contiguous columns")
         L.pack_weight(w, packed[:, col:col + w.shape[1]], s)
         col += w.shape[1]
+    if key is not None:
+        if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+            _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
+        _PACK_CACHE[key] = packed
     return packed
 
 
@@ -122,7 +141,7 @@ class _LinearProjectFn(torch.autograd.Function):
         xb = to_bf16_features(x if x.dim() == 3 else x.unsqueeze(0))
         B, T, D = xb.shape
         H = weight.shape[0]
-        wp = pack_projector([weight], [1.0])
+        wp = pack_projector([weight], [1.0], cache=not ctx.needs_input_grad[1])
         y = torch.empty(B, T, H, dtype=out_dtype, device=x.device)
         if B * T:
             L.proj_fwd([xb], [wp], y, bias0=bias)
@@ -177,7 +196,8 @@ class _FusedConnectorFn(torch.autograd.Function):
             raise ValueError(f"video connector expects input_dim {wv.shape[1]} but stacked video width is {Kv}")
         K = Ka + Kv
         ws = ([wa] if use_a else []) + ([wv] if use_v else [])
-        wp = pack_projector(ws, ([sa] if use_a else []) + ([sv] if use_v else []))
+        wp = pack_projector(ws, ([sa] if use_a else []) + ([sv] if use_v else []),
+                            cache=not any(ctx.needs_input_grad[:4]))
         out_dtype = st["out_dtype"]
         ids = st["input_ids"]
         S = ids.shape[1]

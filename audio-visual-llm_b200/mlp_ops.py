@@ -59,7 +59,7 @@ class FusedMLPConnectorFn(torch.autograd.Function):
         Zs, Hs = [], []
         for x, w1, b1, _, _, _, bit in mods:
             Hd = w1.shape[0]
-            w1p = pack_projector([w1], [1.0])
+            w1p = pack_projector([w1], [1.0], cache=not need_grad)
             h = torch.empty(M, Hd, dtype=bf, device=dev)
             if not need_grad and flags is None:
                 if M:
@@ -78,7 +78,7 @@ class FusedMLPConnectorFn(torch.autograd.Function):
         emb = torch.empty(B, S, H, dtype=out_dtype, device=dev)
         in_place = bool(st["uniform_layout"] and M)
         Y = emb[:, S - N:, :] if in_place else torch.empty(M, H, dtype=out_dtype, device=dev)
-        w2p = pack_projector([m[3] for m in mods], [m[5] for m in mods])
+        w2p = pack_projector([m[3] for m in mods], [m[5] for m in mods], cache=not need_grad)
         wsegs, col = [], 0
         for m in mods:
             wsegs.append(w2p[:, col:col + m[3].shape[1]])

@@ -423,3 +423,26 @@ def test_mlp_modality_connector_module(avc, cuda_dev):
     assert_close(y, ref, "y")
     for t, r, n in zip(conn.mlp_params(), p, ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]):
         assert_close(t.grad, r.grad, n)
+
+
+def test_forward_only_reuses_packed_weights_until_they_change(avc, cuda_dev):
+    """Inference fast path: the bf16 weight pack is cached across no-grad calls and invalidated by an in-place
+    parameter update (torch version counter)."""
+    from audio_visual_llm_b200 import connector_ops as C
+
+    g = torch.Generator().manual_seed(71)
+    conn = avc.ModalityConnector(64, 96, device="cuda:0")
+    x = torch.randn(1, 30, 64, generator=g).to(cuda_dev)
+    C._PACK_CACHE.clear()
+    with torch.no_grad():
+        y1 = conn(x)
+        n1 = len(C._PACK_CACHE)
+        y2 = conn(x)
+        assert len(C._PACK_CACHE) == n1 == 1 and torch.equal(y1, y2)
+        conn.linear.weight.mul_(2.0)  # in-place update bumps the version counter -> re-pack
+        y3 = conn(x)
+        assert len(C._PACK_CACHE) == 2
+    ref = x.cpu() @ conn.linear.weight.detach().cpu().t() + conn.linear.bias.detach().cpu()
+    assert_close(y3, ref, "y after weight update")
+    y4 = conn(x)  # grad mode with trainable weights: never cached
+    assert len(C._PACK_CACHE) == 2 and y4.requires_grad
