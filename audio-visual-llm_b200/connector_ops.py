@@ -133,7 +133,7 @@ class _LinearProjectFn(torch.autograd.Function):
     """y = x . W^T + b on the tcgen05 projector GEMM (one modality; SimpleModalityConnector._forward_impl)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, out_dtype):
+    def forward(ctx, x, weight, bias, out_dtype, cache_pack):
         if ctx.needs_input_grad[0]:
             raise NotImplementedError(
                 "gradient w.r.t. connector inputs (unfrozen towers) is not produced by the B200 path; "
@@ -141,7 +141,7 @@ class _LinearProjectFn(torch.autograd.Function):
         xb = to_bf16_features(x if x.dim() == 3 else x.unsqueeze(0))
         B, T, D = xb.shape
         H = weight.shape[0]
-        wp = pack_projector([weight], [1.0], cache=not ctx.needs_input_grad[1])
+        wp = pack_projector([weight], [1.0], cache=cache_pack)
         y = torch.empty(B, T, H, dtype=out_dtype, device=x.device)
         if B * T:
             L.proj_fwd([xb], [wp], y, bias0=bias)
@@ -165,14 +165,15 @@ class _LinearProjectFn(torch.autograd.Function):
         else:
             dw.zero_()
             db.zero_()
-        return None, dw, db, None
+        return None, dw, db, None, None
 
 
 def linear_project(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     if out_dtype not in _SUPPORTED_OUT:
         raise L.ConnectorError(f"connector output dtype {out_dtype} unsupported on the B200 path (fp32 or bf16)")
     _require_cuda(x, "connector input")
-    return _LinearProjectFn.apply(x, weight, bias, out_dtype)
+    recording = torch.is_grad_enabled() and (weight.requires_grad or bias.requires_grad)
+    return _LinearProjectFn.apply(x, weight, bias, out_dtype, not recording)
 
 
 class _FusedConnectorFn(torch.autograd.Function):
@@ -197,7 +198,7 @@ class _FusedConnectorFn(torch.autograd.Function):
         K = Ka + Kv
         ws = ([wa] if use_a else []) + ([wv] if use_v else [])
         wp = pack_projector(ws, ([sa] if use_a else []) + ([sv] if use_v else []),
-                            cache=not any(ctx.needs_input_grad[:4]))
+                            cache=st["cache_pack"])
         out_dtype = st["out_dtype"]
         ids = st["input_ids"]
         S = ids.shape[1]
@@ -378,6 +379,8 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
               audio_valid=audio_valid, video_valid=video_valid, out_dtype=out_dtype, input_ids=input_ids,
               placeholder_id=placeholder_id, pad_id=pad_id, embed_table=embed_table, labels=labels,
               uniform_layout=uniform_layout)
+    trainable = [p for p in (wa, ba, wv, bv, *(mlp_audio or ()), *(mlp_video or ())) if isinstance(p, torch.Tensor)]
+    st["cache_pack"] = not (torch.is_grad_enabled() and any(p.requires_grad for p in trainable))
     dummy = torch.zeros(0, device=dev)
     if mlp_audio is not None or mlp_video is not None:
         # Linear -> GELU -> Linear per modality: (fc1.weight, fc1.bias, fc2.weight, fc2.bias)

@@ -54,7 +54,7 @@ class FusedMLPConnectorFn(torch.autograd.Function):
         for x, w1, _, w2, _, _, _ in mods:
             if w1.shape[1] != x.shape[1] or w2.shape[1] != w1.shape[0] or w2.shape[0] != H:
                 raise ValueError("MLP projector shapes do not chain: fc1 [Hd, K], fc2 [H, Hd]")
-        need_grad = any(ctx.needs_input_grad[:8])
+        need_grad = not st["cache_pack"]  # gradients are being recorded for the projector parameters
         # ---- layer 1 (+ GELU) per modality
         Zs, Hs = [], []
         for x, w1, b1, _, _, _, bit in mods:
