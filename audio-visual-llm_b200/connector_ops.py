@@ -15,6 +15,7 @@ W = [sa*Wa | sv*Wv] and bias sa*ba*1[audio token] + sv*bv*1[video token] (SURVEY
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -101,10 +102,15 @@ def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float], cac
     GEMM + splice only.  Training re-packs every step: the optimizer has changed the weights."""
     key = None
     if cache:  # the caller is not recording gradients for these weights
-        key = tuple((w.data_ptr(), w._version, tuple(w.shape), float(s)) for w, s in zip(weights, scales))
+        # keyed by tensor identity; a hit also needs the same live objects (weak references: an address can be
+        # reused by another tensor) at the same version counter
+        key = tuple(id(w) for w in weights) + tuple(float(s) for s in scales)
         hit = _PACK_CACHE.get(key)
         if hit is not None:
-            return hit
+            refs, versions, packed = hit
+            if all(r() is w for r, w in zip(refs, weights)) and versions == [w._version for w in weights]:
+                return packed
+            del _PACK_CACHE[key]
     H = weights[0].shape[0]
     K = sum(w.shape[1] for w in weights)
     packed = torch.empty(H, K, dtype=torch.bfloat16, device=weights[0].device)
@@ -117,7 +123,7 @@ def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float], cac
     if key is not None:
         if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
             _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
-        _PACK_CACHE[key] = packed
+        _PACK_CACHE[key] = ([weakref.ref(w) for w in weights], [w._version for w in weights], packed)
     return packed
 
 
