@@ -119,9 +119,13 @@ class ConnectorStep:
         npack = int(self.use_a) + int(self.use_v)
         self.launches_per_step = npack + (3 if self.direct else 5) + 2  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum x2
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
-        self.overlap_comm = True       # N > 1: all-reduce finished gradients while the rest is computed
+        # N > 1: optionally all-reduce the audio-weight span while the video-weight dW launch still runs.  Measured on
+        # B200 x8 (profiles/README.md): NCCL needs ~48+ SMs to run at speed, which the persistent GEMM must give up, so
+        # the overlapped schedule is no faster than one all-reduce after the backward (1.32 ms either way at N = 8,
+        # 1.23 vs 1.24 ms at N = 2).  Off by default.
+        self.overlap_comm = os.environ.get("AVC_OVERLAP_COMM", "0") == "1"
         # SMs the second dW launch leaves to the concurrent NCCL kernel
-        self.comm_reserve_sms = int(os.environ.get("AVC_COMM_RESERVE_SMS", "16"))
+        self.comm_reserve_sms = int(os.environ.get("AVC_COMM_RESERVE_SMS", "48"))
         self._comm_stream = None
         self._side_stream = None
         # run the small HBM-bound kernels of the fused step (text rows + masks, bias sums) on a side stream,
