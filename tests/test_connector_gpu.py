@@ -446,3 +446,132 @@ def test_forward_only_reuses_packed_weights_until_they_change(avc, cuda_dev):
     assert_close(y3, ref, "y after weight update")
     y4 = conn(x)  # grad mode with trainable weights: never cached
     assert len(C._PACK_CACHE) == 1 and y4.requires_grad
+
+
+def test_cfg1_on_gpu_matches_executing_reference_subsample(avc, cuda_dev):
+    """BASELINE.json configs[0] (Whisper-small 768 + CLIP 512 -> 2048, batch 2, 10 s, parity mode) on the B200
+    against the sub-sampled outputs the executing reference produced for the same seeded inputs."""
+    z = np.load(GOLDEN / "ref_cfg1_subsampled.npz")
+    Bc, Ta, Tv, Da, Dv, H = 2, 500, 250, 768, 512, 2048
+    g = torch.Generator().manual_seed(1234 + 1)
+    a = torch.randn(Bc, Ta, Da, generator=g)
+    v = torch.randn(Bc, Tv, Dv, generator=g)
+    up = torch.randn(Bc, Ta, H, generator=torch.Generator().manual_seed(77))
+    chk = np.array([a.double().sum().item(), v.double().sum().item(), up.double().sum().item()])
+    if not np.allclose(chk, z["in.checksum"], rtol=0, atol=1e-6):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    torch.manual_seed(0)
+    la = torch.nn.Linear(Da, H)
+    torch.nn.init.xavier_uniform_(la.weight)
+    lv = torch.nn.Linear(Dv, H)
+    torch.nn.init.xavier_uniform_(lv.weight)
+    gb = torch.Generator().manual_seed(1)
+    ba, bv = torch.randn(H, generator=gb) * 0.02, torch.randn(H, generator=gb) * 0.02
+    if not np.isclose(la.weight.double().sum().item(), float(z["w.checksum.audio_connector"]), atol=1e-6):
+        pytest.skip("weight init RNG stream differs from the fixture's")
+    dev = cuda_dev
+    params = [t.detach().to(dev).requires_grad_(True) for t in (la.weight, ba, lv.weight, bv)]
+    plan = avc.FusePlan(max_seq_len=512, fusion_scale=0.5)
+    for out_dtype in (torch.float32, torch.bfloat16):
+        for p in params:
+            p.grad = None
+        emb, mask, _ = avc.fused_connector(a.to(dev), v.to(dev), *params, plan, out_dtype=out_dtype)
+        emb.backward(up.to(dev, out_dtype))
+        torch.cuda.synchronize()
+        assert_close(emb[:, ::25, ::64], torch.from_numpy(z["out.inputs_embeds[::25, ::64]"]), "inputs_embeds sample")
+        assert int(mask.sum()) == int(z["out.attention_mask.sum"])
+        assert_close(params[0].grad[::32, ::32], torch.from_numpy(z["out.audio_connector.linear.weight.grad[::32, ::32]"]), "dWa")
+        assert_close(params[2].grad[::32, ::32], torch.from_numpy(z["out.video_connector.linear.weight.grad[::32, ::32]"]), "dWv")
+        assert_close(params[1].grad, torch.from_numpy(z["out.audio_connector.linear.bias.grad"]), "dba")
+        assert_close(params[3].grad, torch.from_numpy(z["out.video_connector.linear.bias.grad"]), "dbv")
+
+
+def test_gradients_are_deterministic(avc, cuda_dev):
+    """No split-K atomics anywhere: two runs of the same step give bit-identical dW / db (fused and unfused)."""
+    from audio_visual_llm_b200.engine import ConnectorStep, StepShape
+
+    shape = StepShape(batch=4, audio_frames=400, video_frames=200, audio_dim=128, video_dim=64, hidden=256,
+                      prompt_len=8, vocab=100)
+    plan = avc.FusePlan(fusion="concat", audio_stride=4, video_stride=2, max_seq_len=4096)
+    for fuse in (True, False):
+        eng = ConnectorStep(shape, plan, cuda_dev, seed=1, fuse_gather=fuse)
+        eng.step(allreduce=False)
+        torch.cuda.synchronize()
+        first = eng.bucket.flat.clone()
+        emb1 = eng.emb.clone()
+        eng.bucket.flat.zero_()
+        eng.step(allreduce=False)
+        torch.cuda.synchronize()
+        assert torch.equal(eng.bucket.flat, first) and torch.equal(eng.emb, emb1)
+
+
+@pytest.mark.parametrize("case", ["zero_length_sample", "single_token", "frames_fewer_than_stride", "odd_widths"])
+def test_edge_cases_vs_oracle(avc, cuda_dev, case):
+    """Empty / degenerate inputs: a sample with no valid frames, one token, fewer frames than the stride, widths that
+    are not multiples of the GEMM tile (H = 72, D = 40)."""
+    g = torch.Generator().manual_seed(81)
+    dev = cuda_dev
+    H, V, PH = 72, 40, 39
+    if case == "zero_length_sample":
+        B, Tv, Dv, k = 3, 12, 40, 1
+        lens = [5, 0, 12]
+    elif case == "single_token":
+        B, Tv, Dv, k = 1, 1, 40, 1
+        lens = [1]
+    elif case == "frames_fewer_than_stride":
+        B, Tv, Dv, k = 2, 3, 40, 4   # 3 frames, stride 4 -> one token holding 3 real frames and one zero frame
+        lens = [3, 2]
+    else:
+        B, Tv, Dv, k = 2, 9, 40, 1
+        lens = [9, 4]
+    v = torch.randn(B, Tv, Dv, generator=g)
+    wv = torch.randn(H, k * Dv, generator=g) / (k * Dv) ** 0.5
+    bv = torch.randn(H, generator=g) * 0.1
+    table = torch.randn(V, H, generator=g)
+    spec = O.ConnectorSpec(modality="video", video_stride=k, mask_mode=1, label_mode=1)
+    vv = torch.tensor(lens)
+    wv_c, bv_c = wv.clone().requires_grad_(True), bv.clone().requires_grad_(True)
+    tok, _ = O.connector_tokens(None, v, None, None, wv_c, bv_c, spec, video_valid=vv)
+    ntok = [-(-n // k) for n in lens]
+    S = 3 + max(max(ntok), 1)
+    ids = torch.zeros(B, S, dtype=torch.int64)
+    for b, n in enumerate(ntok):
+        row = torch.randint(1, PH, (S,), generator=g)
+        row[1:1 + n] = PH
+        row[1 + n + 1:] = 0
+        ids[b] = row
+    emb_r, mask_r, lab_r = O.splice_tokens(tok, ids, PH, table, 0, spec, ntok=torch.tensor(ntok))
+    up = torch.randn(emb_r.shape, generator=g)
+    (emb_r * up).sum().backward()
+    wv_d, bv_d = wv.to(dev).requires_grad_(True), bv.to(dev).requires_grad_(True)
+    plan = avc.FusePlan(modality="video", video_stride=k, mask_mode=1, label_mode=1)
+    emb, mask, lab = avc.fused_connector(None, v.to(dev), None, None, wv_d, bv_d, plan, input_ids=ids.to(dev),
+                                         placeholder_id=PH, embed_table=table.to(dev, torch.bfloat16),
+                                         out_dtype=torch.bfloat16, video_lengths=lens, check=True)
+    (emb.float() * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    is_ph = ids == PH
+    if is_ph.any():
+        assert_close(emb[is_ph.to(dev)], emb_r[is_ph], "AV rows")
+    assert torch.equal(emb.cpu()[~is_ph], emb_r[~is_ph].to(torch.bfloat16))
+    assert torch.equal(mask.cpu(), mask_r) and torch.equal(lab.cpu(), lab_r)
+    assert_close(wv_d.grad, wv_c.grad, "dWv")
+    assert_close(bv_d.grad, bv_c.grad, "dbv")
+
+
+def test_all_samples_empty_is_handled(avc, cuda_dev):
+    """M = 0: every sample has zero valid frames -> only text rows, zero gradients, no kernel faults."""
+    dev = cuda_dev
+    H, Dv, V = 64, 32, 20
+    v = torch.randn(2, 6, Dv).to(dev)
+    wv = torch.randn(H, Dv, device=dev, requires_grad=True)
+    bv = torch.randn(H, device=dev, requires_grad=True)
+    ids = torch.randint(1, V - 1, (2, 5)).to(dev)
+    table = torch.randn(V, H).to(dev, torch.bfloat16)
+    plan = avc.FusePlan(modality="video", mask_mode=1)
+    emb, mask, _ = avc.fused_connector(None, v, None, None, wv, bv, plan, input_ids=ids, placeholder_id=V - 1,
+                                       embed_table=table, out_dtype=torch.bfloat16, video_lengths=[0, 0], check=True)
+    emb.float().sum().backward()
+    torch.cuda.synchronize()
+    assert torch.equal(emb, table[ids]) and int(mask.sum()) == 10
+    assert float(wv.grad.abs().max()) == 0.0 and float(bv.grad.abs().max()) == 0.0
