@@ -53,7 +53,6 @@ struct GemmArgs {
   int act;                   // 0 = identity, 1 = GELU (erf form)
 };
 
-size_t gemm_smem_bytes();
 // N tile that minimises (waves x per-tile time) for `m_blocks` x ceil(n_s / bn) tiles on `num_sms` persistent CTAs.
 int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_workers);
 // 2 (default): CTA pairs with tcgen05.mma.cta_group::2 (256-row tiles); 1: single-CTA tiles (AVC_GEMM_CTA_GROUP)
@@ -113,8 +112,6 @@ cudaError_t launch_splice_bwd(const SpliceArgs& args, int num_sms, cudaStream_t 
 // dst_bf16[r, c] = bf16(alpha * src_f32[r, c]),  src ld = src_ld, dst ld = dst_ld (elements)
 cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int64_t dst_ld,
                                int64_t rows, int64_t cols, float alpha, cudaStream_t stream);
-// dst_bf16 = bf16(src_f32) / dst_f32 = float(src_bf16), contiguous n elements
-cudaError_t launch_cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 
 // Column sums of dY over flagged rows, deterministic two-pass:
 //   out0[c] = alpha0 * sum_{r : flag bit0} dY[r, c],  out1[c] = alpha1 * sum_{r : flag bit1} dY[r, c]

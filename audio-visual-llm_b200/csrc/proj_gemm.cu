@@ -463,8 +463,6 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
 
 }  // namespace
 
-size_t gemm_smem_bytes() { return Cfg<1>::SMEM_ALLOC; }
-
 int gemm_cta_group() {
   const int v = env_int("AVC_GEMM_CTA_GROUP", 2);
   return v == 1 ? 1 : 2;
