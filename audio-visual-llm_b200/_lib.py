@@ -26,7 +26,7 @@ EXPORTS = (
 class AvcFeat(C.Structure):
     _fields_ = [
         ("ptr", C.c_void_p), ("batch_stride", C.c_int64), ("frame_stride", C.c_int64),
-        ("frames", C.c_int32), ("dim", C.c_int32), ("stack", C.c_int32), ("reserved", C.c_int32),
+        ("frames", C.c_int32), ("dim", C.c_int32), ("stack", C.c_int32), ("repeat", C.c_int32),
         ("valid_frames", C.c_void_p),
     ]
 
@@ -108,7 +108,8 @@ def mat(t: torch.Tensor) -> AvcMat:
     raise ValueError("expected a 2-D or 3-D tensor")
 
 
-def feat(t: Optional[torch.Tensor], stack: int, valid: Optional[torch.Tensor] = None) -> Optional[AvcFeat]:
+def feat(t: Optional[torch.Tensor], stack: int, valid: Optional[torch.Tensor] = None,
+         repeat: int = 1) -> Optional[AvcFeat]:
     """[batch, frames, dim] bf16 features (any batch/frame stride, dim contiguous) -> avc_feat."""
     if t is None:
         return None
@@ -116,7 +117,7 @@ def feat(t: Optional[torch.Tensor], stack: int, valid: Optional[torch.Tensor] = 
         raise ValueError("features must be bf16 [batch, frames, dim] with contiguous dim")
     if valid is not None and (valid.dtype != torch.int32 or not valid.is_contiguous()):
         raise ValueError("valid_frames must be a contiguous int32 tensor")
-    return AvcFeat(t.data_ptr(), t.stride(0), t.stride(1), t.shape[1], t.shape[2], stack, 0, _ptr(valid))
+    return AvcFeat(t.data_ptr(), t.stride(0), t.stride(1), t.shape[1], t.shape[2], stack, repeat, _ptr(valid))
 
 
 def _mat_array(ms: Sequence[AvcMat]):
@@ -126,8 +127,8 @@ def _mat_array(ms: Sequence[AvcMat]):
 # ------------------------------------------------------------------------------------------ kernels
 def gather_fwd(audio, video, ka: int, kv: int, batch: int, tokens_per_sample: int, a_out: torch.Tensor,
                row_flags: Optional[torch.Tensor] = None, tok_offset: Optional[torch.Tensor] = None,
-               audio_valid=None, video_valid=None) -> None:
-    fa, fv = feat(audio, ka, audio_valid), feat(video, kv, video_valid)
+               audio_valid=None, video_valid=None, audio_repeat: int = 1, video_repeat: int = 1) -> None:
+    fa, fv = feat(audio, ka, audio_valid, audio_repeat), feat(video, kv, video_valid, video_repeat)
     check(load().avc_gather_fwd(
         C.byref(fa) if fa is not None else None, C.byref(fv) if fv is not None else None, C.c_int32(batch),
         C.c_void_p(_ptr(tok_offset)), C.c_int32(tokens_per_sample), C.c_int64(a_out.shape[0]),

@@ -7,7 +7,8 @@ exactly where the reference calls them (clip_whisper_model.py:1098-1103, 1138, 6
 New keyword arguments default to the reference's behaviour:
   fusion="sum" | "concat"      stride=1 (frames stacked per token)      align="index" | "rate"
   audio_stride / video_stride  (override stride/align)                   mask_mode / label_mode (0 = reference)
-`align="rate"` pairs 2 Whisper frames (50 Hz) with 1 CLIP frame (25 fps): k_a = stride, k_v = stride / 2.
+`align="rate"` pairs 2 Whisper frames (50 Hz) with 1 CLIP frame (25 fps): k_a = stride, k_v = stride / 2; at
+stride 1 every video frame is used for two consecutive tokens instead (video_repeat = 2).
 
 There is no CPU fallback (the reference's `"cuda" if torch.cuda.is_available() else "cpu"` default,
 clip_whisper_model.py:91, is removed): the device must be an sm_100 GPU.
@@ -83,12 +84,16 @@ class ClipWhisperModel(nn.Module):
         if video_stride is not None:
             kv = video_stride
         elif align == "rate":
-            if stride % 2:
-                raise ValueError("align='rate' needs an even stride (2 audio frames per video frame)")
-            kv = stride // 2
+            if stride == 1:
+                kv = 1  # every 25 fps video frame is paired with two 50 Hz audio frames (video_repeat = 2)
+            elif stride % 2:
+                raise ValueError("align='rate' needs stride 1 or an even stride (2 audio frames per video frame)")
+            else:
+                kv = stride // 2
         else:
             kv = stride
         self.audio_stride, self.video_stride = ka, kv
+        self.video_repeat = 2 if (align == "rate" and stride == 1 and video_stride is None) else 1
         self.mask_mode, self.label_mode = mask_mode, label_mode
         self.dtype = torch.bfloat16 if use_fp16 else torch.float32  # reference: fp16 if use_fp16 (:164)
 
@@ -144,7 +149,8 @@ class ClipWhisperModel(nn.Module):
     def _plan(self) -> FusePlan:
         return FusePlan(modality=self.modality, fusion=self.fusion, fusion_scale=self.fusion_scale,
                         max_seq_len=self.max_seq_len, audio_stride=self.audio_stride,
-                        video_stride=self.video_stride, mask_mode=self.mask_mode, label_mode=self.label_mode)
+                        video_stride=self.video_stride, video_repeat=self.video_repeat, mask_mode=self.mask_mode,
+                        label_mode=self.label_mode)
 
     # ------------------------------------------------------------------ towers (untouched PyTorch)
     def _whisper_features(self, audio, attention_mask=None):

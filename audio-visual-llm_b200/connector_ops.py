@@ -36,6 +36,8 @@ class FusePlan:
     max_seq_len: int = 256        # caps fused tokens in `both` mode only  (clip_whisper_model.py:427)
     audio_stride: int = 1         # k_a frames stacked per token (new; 1 = reference)
     video_stride: int = 1         # k_v
+    audio_repeat: int = 1         # r_a: every stacked audio token is used r_a times (token j -> stack j // r_a)
+    video_repeat: int = 1         # r_v: 2 pairs 25 fps video with 50 Hz audio at stride 1 (rate alignment)
     mask_mode: int = 0            # 0 all ones (clip_whisper_model.py:460) | 1 valid tokens only
     label_mode: int = 0           # 0 reference eval rule | 1 also -100 on placeholders / pad ids
 
@@ -46,6 +48,8 @@ class FusePlan:
             raise ValueError(f"fusion must be sum|concat, got {self.fusion!r}")
         if self.audio_stride < 1 or self.video_stride < 1:
             raise ValueError("strides must be >= 1")
+        if self.audio_repeat < 1 or self.video_repeat < 1:
+            raise ValueError("repeats must be >= 1")
 
     def scales(self, use_a: bool, use_v: bool) -> Tuple[float, float]:
         if use_a and use_v and self.fusion == "sum":
@@ -54,8 +58,8 @@ class FusePlan:
 
     def tokens(self, Ta: Optional[int], Tv: Optional[int]) -> int:
         """Fused tokens for Ta audio / Tv video frames: ceil(T/k) per stream, max, capped in `both` mode."""
-        na = -(-Ta // self.audio_stride) if Ta is not None else None
-        nv = -(-Tv // self.video_stride) if Tv is not None else None
+        na = -(-Ta // self.audio_stride) * self.audio_repeat if Ta is not None else None
+        nv = -(-Tv // self.video_stride) * self.video_repeat if Tv is not None else None
         if na is not None and nv is not None:
             return min(self.max_seq_len, max(na, nv))
         return na if na is not None else nv
@@ -219,7 +223,8 @@ class _FusedConnectorFn(torch.autograd.Function):
             b0, b1, s0, s1 = ba, None, sa, 0.0
         else:  # video only: its "present" flag is bit 1
             b0, b1, s0, s1 = None, bv, 0.0, sv
-        direct = st["tok_offset"] is None and _stack_is_free_view(audio, ka, N) and _stack_is_free_view(video, kv, N)
+        direct = (st["tok_offset"] is None and plan.audio_repeat == 1 and plan.video_repeat == 1
+                  and _stack_is_free_view(audio, ka, N) and _stack_is_free_view(video, kv, N))
         if direct:
             # Dense streams whose frame counts divide by the stride: stacking k frames is a free reshape
             # [B, T, D] -> [B*T/k, k*D], so the GEMM reads the tower outputs in place through one TMA descriptor
@@ -236,7 +241,7 @@ class _FusedConnectorFn(torch.autograd.Function):
             xs = ([A[:, :Ka]] if use_a else []) + ([A[:, Ka:]] if use_v else [])
             if M:
                 L.gather_fwd(audio, video, ka, kv, B, N, A, flags, st["tok_offset"], st["audio_valid"],
-                             st["video_valid"])
+                             st["video_valid"], plan.audio_repeat, plan.video_repeat)
                 # 2. projector: one GEMM over [a ; v]
                 L.proj_fwd([A], [wp], Y, bias0=b0, bias1=b1, bias_scale0=s0, bias_scale1=s1, row_flags=flags)
         # 3. splice into the LLM input-embedding sequence + masks

@@ -145,8 +145,11 @@ int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t batch, 
   memset(&g, 0, sizeof(g));
   const avc_feat* f[2] = {audio, video};
   int64_t k_total = 0;
+  g.rep[0] = g.rep[1] = 1;
   for (int i = 0; i < 2; ++i) {
     if (f[i] == nullptr || f[i]->ptr == nullptr) continue;
+    if (f[i]->repeat < 0) return fail(AVC_ERR_INVALID, "gather: negative repeat");
+    g.rep[i] = f[i]->repeat > 0 ? f[i]->repeat : 1;
     if (f[i]->dim <= 0 || f[i]->dim % 8 != 0)
       return fail(AVC_ERR_INVALID, "gather: feature dim %d must be a positive multiple of 8", f[i]->dim);
     if (f[i]->stack < 1 || f[i]->frames < 0) return fail(AVC_ERR_INVALID, "gather: bad stack / frames");

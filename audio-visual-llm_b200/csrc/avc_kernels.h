@@ -69,6 +69,7 @@ struct GatherArgs {
   int frame_bytes[2];         // D * sizeof(bf16)
   int frames[2];              // T per modality (upper bound on valid frames)
   int k[2];                   // frames stacked per token
+  int rep[2];                 // each stacked token is used rep times (token j -> stack j / rep)
   const int32_t* len[2];      // optional per-sample valid frame counts (device), nullptr: frames[i]
   const int32_t* tok_offset;  // [B+1] packed row offsets (device), nullptr: uniform tokens_per_sample
   int tokens_per_sample;      // uniform mode

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_const
       locate_row(a, m, b, j);
       const int mod = it.mod;
       const int len = valid_len(a, mod, b);
-      const int64_t f0 = static_cast<int64_t>(j) * a.k[mod];
+      const int64_t f0 = static_cast<int64_t>(j / a.rep[mod]) * a.k[mod];
       int64_t nv = len - f0;
       nv = nv < 0 ? 0 : (nv > a.k[mod] ? a.k[mod] : nv);
       it.nvalid = static_cast<int>(nv);
@@ -100,11 +100,11 @@ __global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_const
         uint8_t fl = 0;
         if (a.src[0] != nullptr) {
           const int la = (mod == 0) ? len : valid_len(a, 0, b);
-          if (static_cast<int64_t>(j) * a.k[0] < la) fl |= 1;
+          if (static_cast<int64_t>(j / a.rep[0]) * a.k[0] < la) fl |= 1;
         }
         if (a.src[1] != nullptr) {
           const int lv = (mod == 1) ? len : valid_len(a, 1, b);
-          if (static_cast<int64_t>(j) * a.k[1] < lv) fl |= 2;
+          if (static_cast<int64_t>(j / a.rep[1]) * a.k[1] < lv) fl |= 2;
         }
         a.row_flags[m] = fl;
       }

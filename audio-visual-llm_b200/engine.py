@@ -114,7 +114,8 @@ class ConnectorStep:
         # rows P .. P+N-1).  Otherwise: gather -> GEMM, splice-bwd -> GEMM.
         def free(frames, k):
             return frames % k == 0 and frames // k == self.N
-        self.direct = bool(fuse_gather and (not self.use_a or free(s.audio_frames, p.audio_stride))
+        self.direct = bool(fuse_gather and p.audio_repeat == 1 and p.video_repeat == 1
+                           and (not self.use_a or free(s.audio_frames, p.audio_stride))
                            and (not self.use_v or free(s.video_frames, p.video_stride)))
         npack = int(self.use_a) + int(self.use_v)
         self.launches_per_step = npack + (3 if self.direct else 5) + 2  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum x2
@@ -189,7 +190,8 @@ class ConnectorStep:
             L.pack_weight(self.wv, self.wp[:, col:], self.sv)
         if not self.direct:
             self._timed("gather", lambda: L.gather_fwd(self.audio, self.video, p.audio_stride, p.video_stride,
-                                                       self.shape.batch, self.N, self.A, self.flags))
+                                                       self.shape.batch, self.N, self.A, self.flags,
+                                                       audio_repeat=p.audio_repeat, video_repeat=p.video_repeat))
         if self.use_a and self.use_v:
             b0, b1, s0, s1 = self.ba, self.bv, self.sa, self.sv
         elif self.use_a:

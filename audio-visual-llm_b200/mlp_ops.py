@@ -34,7 +34,8 @@ class FusedMLPConnectorFn(torch.autograd.Function):
         H = (w2a if use_a else w2v).shape[0]
         out_dtype = st["out_dtype"]
         bf = torch.bfloat16
-        direct = st["tok_offset"] is None and _stack_is_free_view(audio, ka, N) and _stack_is_free_view(video, kv, N)
+        direct = (st["tok_offset"] is None and plan.audio_repeat == 1 and plan.video_repeat == 1
+                  and _stack_is_free_view(audio, ka, N) and _stack_is_free_view(video, kv, N))
         flags = None
         if direct:
             xa = audio.view(M, Ka) if use_a else None
@@ -44,7 +45,7 @@ class FusedMLPConnectorFn(torch.autograd.Function):
             flags = torch.empty(M, dtype=torch.uint8, device=dev)
             if M:
                 L.gather_fwd(audio, video, ka, kv, B, N, A, flags, st["tok_offset"], st["audio_valid"],
-                             st["video_valid"])
+                             st["video_valid"], plan.audio_repeat, plan.video_repeat)
             xa = A[:, :Ka] if use_a else None
             xv = A[:, Ka:] if use_v else None
         if use_a:

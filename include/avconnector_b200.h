@@ -52,7 +52,9 @@ typedef struct avc_feat {
   int32_t frames;              /* T */
   int32_t dim;                 /* D, multiple of 8 */
   int32_t stack;               /* k >= 1 frames stacked per token (k = 1: reference behaviour) */
-  int32_t reserved;
+  int32_t repeat;              /* r >= 1 (0 = 1): token j reads the stack starting at frame (j / r) * k, i.e. every
+                                  stacked token is used r times -- pairs a slower stream with a faster one
+                                  (25 fps video against 50 Hz audio at stride 1: r = 2) */
   const int32_t* valid_frames; /* [batch] per-sample valid frame count, or NULL (= frames) */
 } avc_feat;
 
@@ -67,7 +69,8 @@ typedef struct avc_mat {
 } avc_mat;
 
 /* ---- gather: temporal align + stride-k stack + concat (HBM-bound, TMA bulk copies) ---------------
- * A[m, :] = [audio[b, ka*j .. ka*j+ka-1, :] ; video[b, kv*j .. kv*j+kv-1, :]], m = tok_offset[b] + j,
+ * A[m, :] = [audio[b, ka*ja .. ka*ja+ka-1, :] ; video[b, kv*jv .. kv*jv+kv-1, :]], ja = j / ra, jv = j / rv,
+ * m = tok_offset[b] + j,
  * frames past the valid length are zero.  row_flags[m] bit0/bit1 = row has an audio / video token.
  * Replaces _pad_or_truncate + index alignment (clip_whisper_model.py:320-374, 424-431), moved in
  * front of the projection (exact: padding rows are zero and their bias is masked via row_flags). */

@@ -150,6 +150,8 @@ class ConnectorSpec:
     max_seq_len: int = 256          # cap on fused tokens in `both` mode (clip_whisper_model.py:427)
     audio_stride: int = 1           # k_a frames stacked per token     (new; 1 = reference)
     video_stride: int = 1           # k_v
+    audio_repeat: int = 1           # each stacked token used r times (token j -> stack j // r)   (new; 1 = reference)
+    video_repeat: int = 1
     mask_mode: int = 0              # 0 all ones (reference :460) | 1 valid tokens only
     label_mode: int = 0             # 0 reference eval rule | 1 also -100 on placeholders / pads
     act: int = 0                    # 0 linear projector | 1 erf-GELU after the (first) projection
@@ -170,8 +172,8 @@ def stack_frames(x: torch.Tensor, k: int, ntok: int, valid: Optional[torch.Tenso
 
 def token_counts(spec: ConnectorSpec, Ta: Optional[int], Tv: Optional[int]) -> int:
     """Fused tokens per sample: ceil(T/k) per stream, max over streams, capped only in `both` mode."""
-    na = -(-Ta // spec.audio_stride) if Ta is not None else None
-    nv = -(-Tv // spec.video_stride) if Tv is not None else None
+    na = -(-Ta // spec.audio_stride) * spec.audio_repeat if Ta is not None else None
+    nv = -(-Tv // spec.video_stride) * spec.video_repeat if Tv is not None else None
     if na is not None and nv is not None:
         return min(spec.max_seq_len, max(na, nv))
     return na if na is not None else nv
@@ -194,15 +196,15 @@ def connector_tokens(audio_feats, video_feats, wa, ba, wv, bv, spec: ConnectorSp
     out = None
     flags = torch.zeros(B, N, dtype=torch.uint8)
     j = torch.arange(N).unsqueeze(0)
-    for bit, (use, x, w, b, k, valid, s) in enumerate([
-            (use_a, audio_feats, wa, ba, spec.audio_stride, audio_valid, sa),
-            (use_v, video_feats, wv, bv, spec.video_stride, video_valid, sv)]):
+    for bit, (use, x, w, b, k, r, valid, s) in enumerate([
+            (use_a, audio_feats, wa, ba, spec.audio_stride, spec.audio_repeat, audio_valid, sa),
+            (use_v, video_feats, wv, bv, spec.video_stride, spec.video_repeat, video_valid, sv)]):
         if not use:
             continue
         T = x.shape[1]
         n_valid = torch.full((B,), T) if valid is None else valid.clamp(0, T).to(torch.long)
-        present = (j * k) < n_valid.unsqueeze(1)  # token has at least one real frame
-        stacked = stack_frames(x.to(w.dtype), k, N, valid)
+        present = ((j // r) * k) < n_valid.unsqueeze(1)  # token has at least one real frame
+        stacked = stack_frames(x.to(w.dtype), k, -(-N // r), valid).repeat_interleave(r, dim=1)[:, :N]
         y = s * (stacked @ w.t() + b * present.unsqueeze(-1).to(w.dtype))
         out = y if out is None else out + y
         flags |= present.to(torch.uint8) << bit

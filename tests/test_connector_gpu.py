@@ -575,3 +575,34 @@ def test_all_samples_empty_is_handled(avc, cuda_dev):
     torch.cuda.synchronize()
     assert torch.equal(emb, table[ids]) and int(mask.sum()) == 10
     assert float(wv.grad.abs().max()) == 0.0 and float(bv.grad.abs().max()) == 0.0
+
+
+def test_rate_alignment_at_stride_one_repeats_video_frames(avc, cuda_dev):
+    """align="rate", stride 1: token j = [audio frame j ; video frame j // 2] (50 Hz audio against 25 fps video)."""
+    g = torch.Generator().manual_seed(91)
+    B, Ta, Tv, Da, Dv, H = 2, 21, 10, 32, 16, 64   # 21 audio frames vs 10 video frames -> 20 video tokens, 21 tokens
+    a, v = torch.randn(B, Ta, Da, generator=g), torch.randn(B, Tv, Dv, generator=g)
+    wa, ba, wv, bv = _rand_params(g, H, Da, Dv)
+    spec = O.ConnectorSpec(fusion="sum", fusion_scale=0.6, video_repeat=2, max_seq_len=64)
+    tok_r, flags_r = O.connector_tokens(a, v, wa, ba, wv, bv, spec)
+    assert tok_r.shape[1] == 21 and flags_r[0, 20] == 1 and flags_r[0, 19] == 3
+    # hand check of the pairing: token 5 uses video frame 2
+    manual = 0.6 * (a[:, 5] @ wa.t() + ba) + 0.4 * (v[:, 2] @ wv.t() + bv)
+    assert torch.allclose(tok_r[:, 5], manual, atol=1e-5)
+    up = torch.randn(tok_r.shape, generator=g)
+    grads_r = O.connector_grads(a, v, wa, ba, wv, bv, spec, up)
+    dev = cuda_dev
+    params = [t.to(dev).requires_grad_(True) for t in (wa, ba, wv, bv)]
+    plan = avc.FusePlan(fusion="sum", fusion_scale=0.6, video_repeat=2, max_seq_len=64)
+    emb, mask, _ = avc.fused_connector(a.to(dev), v.to(dev), *params, plan, out_dtype=torch.float32, check=True)
+    (emb * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(emb, tok_r, "tokens")
+    for p, gr, n in zip(params, grads_r, ["dWa", "dba", "dWv", "dbv"]):
+        assert_close(p.grad, gr, n)
+    # the model maps align="rate", stride=1 onto video_repeat = 2
+    m_kw = dict(device="cuda:0", modality="both", align="rate", stride=1, _provided_tokenizer=SimpleNamespace(pad_token_id=0),
+                _provided_llm=StubLLM(torch.zeros(8, H)).to(dev), _provided_whisper=StubWhisper(Da).to(dev),
+                _provided_clip=StubClip(Dv).to(dev))
+    m = avc.ClipWhisperModel(**m_kw)
+    assert (m.audio_stride, m.video_stride, m.video_repeat) == (1, 1, 2) and m._plan().video_repeat == 2
