@@ -63,3 +63,28 @@ def test_no_gpu_means_loud_failure_not_fallback(avc):
 def test_product_never_imports_the_oracle():
     for p in (ROOT / "audio-visual-llm_b200").rglob("*.py"):
         assert "oracle" not in p.read_text().replace("oracle/", ""), f"{p} references the oracle"
+
+
+def test_plain_c_program_links_against_the_abi(avc, tmp_path):
+    """The boundary is a C ABI: a C99 translation unit that only includes include/avconnector_b200.h compiles,
+    links against the shared library and runs (without a GPU the device check reports an error, it does not crash)."""
+    import shutil
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc unavailable")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "avconnector_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  avc_feat f; avc_mat m; avc_splice s; (void)f; (void)m; (void)s;\n"
+        '  printf("abi=%d ws=%zu\\n", avc_abi_version(), avc_colsum_workspace_bytes(4096));\n'
+        "  int rc = avc_device_check(0);\n"
+        '  printf("device_check=%d msg=%s\\n", rc, avc_last_error());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    lib_dir = avc._lib.lib_path().parent
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                        "-L", str(lib_dir), "-lavconnector_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi=1" in out.stdout and "device_check=" in out.stdout
