@@ -194,6 +194,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   memset(&g, 0, sizeof(g));
   g.nseg = nseg;
   const int cg = avc::gemm_cta_group();
+  const int mt = avc::gemm_m_subtiles(cg, avc::GEMM_TN);
   // scatter mode: the operand rows are packed [B*N, K] while Y is a strided [B][N][H] region (e.g. the AV rows of
   // inputs_embeds): M tiles run over the packed rows and the epilogue splits boxes at sample boundaries
   const bool scatter = a[0].batches == 1 && y->batches > 1;
@@ -201,7 +202,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   const int64_t m_batches = scatter ? 1 : y->batches;
   if (scatter && row_flags == nullptr && (flag_rows0 < m_rows || flag_rows1 < m_rows) && (bias0 || bias1))
     return fail(AVC_ERR_INVALID, "proj_fwd: analytic row flags are per packed row in scatter mode; pass row_flags");
-  g.m_tiles_per_batch = static_cast<int>(ceil_div(m_rows, avc::GEMM_BM * cg));
+  g.m_tiles_per_batch = static_cast<int>(ceil_div(m_rows, avc::GEMM_BM * cg * mt));
   g.num_m_blocks = static_cast<int>(m_batches) * g.m_tiles_per_batch;
   if (scatter)
     if (int rc = make_map3d(&g.md_row, y->ptr, y_is_fp32 != 0, N, y->rows, y->batches, y->row_stride,
@@ -220,7 +221,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
     if (s > 0 && a[s].batches != a[0].batches) return fail(AVC_ERR_INVALID, "proj_fwd: segments disagree on batching");
     if (a[s].cols % 8 != 0) return fail(AVC_ERR_INVALID, "proj_fwd: K must be a multiple of 8");
     if (int rc = make_map3d(&g.ma[s], a[s].ptr, false, a[s].cols, a[s].rows, a[s].batches, a[s].row_stride,
-                            a[s].batch_stride, avc::GEMM_BK, avc::GEMM_BM, "proj_fwd A"))
+                            a[s].batch_stride, avc::GEMM_BK, avc::GEMM_BM * mt, "proj_fwd A"))
       return rc;
     if (int rc = make_map3d(&g.mb[s], w[s].ptr, false, w[s].cols, w[s].rows, 1, w[s].row_stride, 0,
                             avc::GEMM_BK, g.bn / cg, "proj_fwd W"))
@@ -245,7 +246,8 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   g.act = act;
   if ((bias0 && (reinterpret_cast<uintptr_t>(bias0) & 15)) || (bias1 && (reinterpret_cast<uintptr_t>(bias1) & 15)))
     return fail(AVC_ERR_INVALID, "proj_fwd: bias pointers must be 16-byte aligned");
-  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, y_is_fp32 != 0, cg, di.num_sms, static_cast<cudaStream_t>(stream));
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, y_is_fp32 != 0, cg, mt, di.num_sms,
+                                   static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_fwd launch");
   return AVC_OK;
 }
@@ -272,7 +274,8 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
   int64_t n_ext[2] = {0, 0};
   for (int s = 0; s < nseg; ++s) n_ext[s] = x[s].cols;
   const int cg = avc::gemm_cta_group();
-  g.num_m_blocks = static_cast<int>(ceil_div(H, avc::GEMM_BM * cg));
+  const int mt = avc::gemm_m_subtiles(cg, avc::GEMM_NT);
+  g.num_m_blocks = static_cast<int>(ceil_div(H, avc::GEMM_BM * cg * mt));
   g.bn = avc::pick_gemm_bn(g.num_m_blocks, n_ext, nseg, di.num_sms / cg);
   for (int s = 0; s < nseg; ++s) {
     if (x[s].batches != dy->batches) return fail(AVC_ERR_INVALID, "proj_bwd_dw: segment %d: batch mismatch", s);
@@ -296,7 +299,7 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
   g.red_kblocks_per_batch = static_cast<int>(ceil_div(red_rows, avc::GEMM_BK));
   g.a_row_base = dy_row_base;
   g.d_rows = static_cast<int>(H);
-  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, cg, di.num_sms, static_cast<cudaStream_t>(stream));
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, cg, mt, di.num_sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_bwd_dw launch");
   return AVC_OK;
 }

@@ -57,9 +57,13 @@ struct GemmArgs {
 int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_workers);
 // 2 (default): CTA pairs with tcgen05.mma.cta_group::2 (256-row tiles); 1: single-CTA tiles (AVC_GEMM_CTA_GROUP)
 int gemm_cta_group();
-// num_m_blocks counts blocks of cta_group * GEMM_BM rows; the B tensor-map box must hold bn / cta_group rows (TN)
-cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int num_sms,
-                        cudaStream_t stream);
+// M sub-tiles per CTA of the pair kernel: 2 = every CTA stages 256 rows of A -> 512 x bn pair tiles (default for
+// the dW GEMM), 1 = 256 x bn pair tiles (default for the forward).  AVC_GEMM_MT[_TN|_NT] override.
+int gemm_m_subtiles(int cta_group, GemmMode mode);
+// num_m_blocks counts blocks of cta_group * m_subtiles * GEMM_BM rows; the TN tensor-map boxes must hold
+// m_subtiles * GEMM_BM rows of A and bn / cta_group rows of B
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int m_subtiles,
+                        int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------ gather (align + stack + concat)
 struct GatherArgs {

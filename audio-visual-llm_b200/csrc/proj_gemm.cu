@@ -39,11 +39,17 @@ constexpr int kThreads = 32 * (2 + EPI_WARPS);
 constexpr int MN_ATOM_BYTES = BK * 128;  // one 64-wide MN-major atom column: BK rows x 128 B
 constexpr int kMaxStages = 6;
 
-template <int CG>
+// MT = M sub-tiles per CTA.  MT = 2 (CTA pairs only): each CTA stages 256 rows of A and the pair computes a
+// 512 x bn tile as two M = 256 UMMAs per K step that share the B operand; the two accumulators fill all 512 TMEM
+// columns (no accumulator double buffering).  Operand bytes staged per FLOP drop by a quarter (the B half is
+// written once and read by both UMMAs), which is what bounds the 256 x 256 kernel.
+template <int CG, int MT>
 struct Cfg {
-  static constexpr int kStages = CG == 2 ? 6 : 4;
+  static constexpr int kStages = CG == 2 ? (MT == 2 ? 4 : 6) : 4;
+  static constexpr int A_BYTES = A_STAGE_BYTES * MT;        // 16 KB / 32 KB
   static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;  // 32 KB / 16 KB
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  static constexpr int kAcc = MT == 2 ? 1 : 2;              // accumulator stages in TMEM
   static constexpr int SMEM_USED = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static constexpr int SMEM_ALLOC = SMEM_USED + 1024;  // slack for manual 1024-B alignment
   static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -51,16 +57,21 @@ struct Cfg {
 };
 static_assert(kAccStages * BN <= kTmemCols, "accumulators exceed TMEM");
 static_assert((2 * kMaxStages + 2 * kAccStages) * 8 + 8 <= BAR_BYTES, "barrier area too small");
+static_assert(2 * BN <= kTmemCols, "two M sub-tile accumulators exceed TMEM");
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int MODE, bool OUT_F32, int CG>
+template <int MODE, bool OUT_F32, int CG, int MT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
-  using C = Cfg<CG>;
+  using C = Cfg<CG, MT>;
   constexpr int kStages = C::kStages;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int A_BYTES = C::A_BYTES;
+  constexpr int kAcc = C::kAcc;
+  constexpr int TILE_M = BM * CG * MT;  // rows of one work item
+  static_assert(MT == 1 || CG == 2, "MT = 2 needs the CTA-pair kernel");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_epi = smem_base + kStages * STAGE_BYTES;
@@ -89,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), 1);
       }
-      for (int a = 0; a < kAccStages; ++a) {
+      for (int a = 0; a < kAcc; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), EPI_WARPS * CG);  // epilogue warps of every CTA of the group
       }
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     n_blk = r / rows_in_group;
   };
   // bytes this CTA's TMA loads deliver per stage (OOB parts of a box are zero-filled and still counted)
-  const uint32_t cta_tx = A_STAGE_BYTES + (MODE == GEMM_TN ? static_cast<uint32_t>(bn_cta) * (BK * 2)
+  const uint32_t cta_tx = A_BYTES + (MODE == GEMM_TN ? static_cast<uint32_t>(bn_cta) * (BK * 2)
                                                             : static_cast<uint32_t>(nb_boxes) * MN_ATOM_BYTES);
   const int total_kb = (MODE == GEMM_TN)
                            ? (args.seg_kblocks[0] + (args.nseg > 1 ? args.seg_kblocks[1] : 0))
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         const int w_cta = width / CG;  // B rows / columns of this CTA that the MMA reads
         if (MODE == GEMM_TN) {
           const int b = m_blk / args.m_tiles_per_batch;
-          const int r0 = (m_blk % args.m_tiles_per_batch) * (BM * CG) + static_cast<int>(rank) * BM;
+          const int r0 = (m_blk % args.m_tiles_per_batch) * TILE_M + static_cast<int>(rank) * (BM * MT);
           const int n0 = n_blk * bn + n_off + static_cast<int>(rank) * w_cta;
           for (int seg = 0; seg < args.nseg; ++seg) {
             for (int kb = 0; kb < args.seg_kblocks[seg]; ++kb) {
@@ -173,12 +184,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               if (leader) mbar_arrive_expect_tx(full_bar(stage), cta_tx * CG);
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               load(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b, pol_a);
-              load(sa + A_STAGE_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0, pol_b);
+              load(sa + A_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0, pol_b);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
         } else {
-          const int m0 = m_blk * (BM * CG) + static_cast<int>(rank) * BM;
+          const int m0 = m_blk * TILE_M + static_cast<int>(rank) * (BM * MT);
           const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
           const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off + static_cast<int>(rank) * w_cta;
           for (int bb = 0; bb < args.red_batches; ++bb) {
@@ -188,11 +199,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               const int row = kb * BK;
 #pragma unroll
-              for (int i = 0; i < BM / 64; ++i)
+              for (int i = 0; i < BM * MT / 64; ++i)
                 load(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64, args.a_row_base + row, bb,
                      pol_a);
               for (int i = 0; i < nb_boxes; ++i)
-                load(sa + A_STAGE_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage), nl0 + i * 64, row, bb,
+                load(sa + A_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage), nl0 + i * 64, row, bb,
                      pol_b);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
@@ -211,29 +222,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         const uint32_t idesc = make_idesc_bf16(BM * CG, width, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < total_kb; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            uint64_t da, db;
-            if (MODE == GEMM_TN) {
-              // K-major: 8-row x 128-B swizzle atoms stacked along M/N (SBO = 1024 B); stepping
-              // UMMA_K = 16 elements inside the 128-B row is +32 B on the start address.
-              da = make_smem_desc_sw128(sa + kk * (UMMA_K * 2), 0, 1024);
-              db = make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 0, 1024);
-            } else {
-              // MN-major: each contraction row is one 128-B swizzle row of 64 M/N elements;
-              // 8 rows per atom (SBO = 1024 B), next 64 M/N elements at LBO = BK*128 B;
-              // UMMA_K = 16 contraction rows = +2048 B.
-              da = make_smem_desc_sw128(sa + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
-              db = make_smem_desc_sw128(sb + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
+          for (int h = 0; h < MT; ++h) {
+            // MT = 2: rows [128 h, 128 h + 128) of each CTA's A stage -> accumulator h (TMEM columns 256 h ..)
+            const uint32_t d_tmem = tmem_base + (MT == 2 ? h * BN : acc * BN);
+            const uint32_t sah = sa + h * A_STAGE_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              uint64_t da, db;
+              if (MODE == GEMM_TN) {
+                // K-major: 8-row x 128-B swizzle atoms stacked along M/N (SBO = 1024 B); stepping
+                // UMMA_K = 16 elements inside the 128-B row is +32 B on the start address.
+                da = make_smem_desc_sw128(sah + kk * (UMMA_K * 2), 0, 1024);
+                db = make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 0, 1024);
+              } else {
+                // MN-major: each contraction row is one 128-B swizzle row of 64 M/N elements;
+                // 8 rows per atom (SBO = 1024 B), next 64 M/N elements at LBO = BK*128 B;
+                // UMMA_K = 16 contraction rows = +2048 B.
+                da = make_smem_desc_sw128(sah + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
+                db = make_smem_desc_sw128(sb + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
+              }
+              if (CG == 2) umma_f16_cg2(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
             }
-            if (CG == 2) umma_f16_cg2(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
-            else umma_f16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
           if (CG == 2) umma_commit_cg2(empty_bar(stage), 3);
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         // accumulator complete -> epilogue (of both CTAs)
         if (CG == 2) umma_commit_cg2(tfull_bar(acc), 3);
         else umma_commit(tfull_bar(acc));
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
       }
     }
     __syncwarp();
@@ -257,17 +273,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       int m_blk, n_blk, n_off, width;
       decode(w, m_blk, n_blk, n_off, width);
       const int nchunk = width / COLS;
-      int out_row0, out_batch, out_col0, seg = 0;
+      int tile_row0, out_batch, out_col0, seg = 0;
       if (MODE == GEMM_TN) {
         out_batch = m_blk / args.m_tiles_per_batch;
-        out_row0 = (m_blk % args.m_tiles_per_batch) * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
+        tile_row0 = (m_blk % args.m_tiles_per_batch) * TILE_M + static_cast<int>(rank) * (BM * MT) + q * 32;
         out_col0 = n_blk * bn + n_off;
       } else {
         out_batch = 0;
-        out_row0 = m_blk * (BM * CG) + static_cast<int>(rank) * BM + q * 32;
+        tile_row0 = m_blk * TILE_M + static_cast<int>(rank) * (BM * MT) + q * 32;
         seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
         out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off;
       }
+      const float alpha = args.alpha[seg];
+      const int ncols = args.d_cols[seg];
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int h = 0; h < MT; ++h) {  // MT = 2: accumulator h holds rows [128 h, 128 h + 128) of this CTA
+      const int out_row0 = tile_row0 + h * BM;
       const int my_row = out_row0 + lane;
       float f0 = 0.f, f1 = 0.f;
       if (MODE == GEMM_TN) {
@@ -284,12 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (args.bias0 == nullptr) f0 = 0.f;
         if (args.bias1 == nullptr) f1 = 0.f;
       }
-      const float alpha = args.alpha[seg];
-      const int ncols = args.d_cols[seg];
-
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_row = tmem_base + (MT == 2 ? h * BN : acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
       for (int c = 0; c < nchunk; ++c) {
@@ -377,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
         buf ^= 1u;
       }
+      }  // h
       // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the issuer
       tc_fence_before();
       __syncwarp();
@@ -384,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
         else mbar_arrive(tempty_bar(acc));
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0 || (MODE == GEMM_TN && args.scatter_rows > 0)) bulk_wait_all<0>();
     __syncwarp();
@@ -405,7 +426,7 @@ int env_int(const char* name, int dflt) {
   return e != nullptr ? atoi(e) : dflt;
 }
 
-template <int CG>
+template <int CG, int MT>
 cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
   GemmArgs args = args_in;
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
@@ -440,12 +461,12 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
     }
   }
   auto run = [&](auto kern) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG, MT>::SMEM_ALLOC);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * CG);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<CG>::SMEM_ALLOC;
+    cfg.dynamicSmemBytes = Cfg<CG, MT>::SMEM_ALLOC;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -457,8 +478,8 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
     return cudaLaunchKernelEx(&cfg, kern, args);
   };
   if (mode == GEMM_TN)
-    return out_fp32 ? run(gemm_kernel<GEMM_TN, true, CG>) : run(gemm_kernel<GEMM_TN, false, CG>);
-  return out_fp32 ? run(gemm_kernel<GEMM_NT, true, CG>) : run(gemm_kernel<GEMM_NT, false, CG>);
+    return out_fp32 ? run(gemm_kernel<GEMM_TN, true, CG, MT>) : run(gemm_kernel<GEMM_TN, false, CG, MT>);
+  return out_fp32 ? run(gemm_kernel<GEMM_NT, true, CG, MT>) : run(gemm_kernel<GEMM_NT, false, CG, MT>);
 }
 
 }  // namespace
@@ -466,6 +487,16 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
 int gemm_cta_group() {
   const int v = env_int("AVC_GEMM_CTA_GROUP", 2);
   return v == 1 ? 1 : 2;
+}
+
+int gemm_m_subtiles(int cta_group, GemmMode mode) {
+  if (cta_group != 2) return 1;
+  // Measured on B200 at the cfg2 shapes (profiles/README.md): the forward (47 x 16 pair tiles of 256 rows) loses
+  // more to wave quantisation and the exposed epilogue with 512-row tiles than it gains from the lower operand
+  // traffic; dW (long reduction, few tiles) gains 10 %.
+  const int dflt = mode == GEMM_NT ? 2 : 1;
+  const int v = env_int(mode == GEMM_NT ? "AVC_GEMM_MT_NT" : "AVC_GEMM_MT_TN", env_int("AVC_GEMM_MT", dflt));
+  return v == 2 ? 2 : 1;
 }
 
 int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_workers) {
@@ -488,13 +519,14 @@ int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_worker
   return best;
 }
 
-cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int num_sms,
-                        cudaStream_t stream) {
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int m_subtiles,
+                        int num_sms, cudaStream_t stream) {
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
   if (num_tiles <= 0) return cudaSuccess;
   if (args.bn < 64 || args.bn > BN || args.bn % 64 != 0) return cudaErrorInvalidValue;
-  if (cta_group == 2) return launch_cg<2>(args, mode, out_fp32, num_sms, stream);
-  return launch_cg<1>(args, mode, out_fp32, num_sms, stream);
+  if (cta_group == 2 && m_subtiles == 2) return launch_cg<2, 2>(args, mode, out_fp32, num_sms, stream);
+  if (cta_group == 2) return launch_cg<2, 1>(args, mode, out_fp32, num_sms, stream);
+  return launch_cg<1, 1>(args, mode, out_fp32, num_sms, stream);
 }
 
 }  // namespace avc

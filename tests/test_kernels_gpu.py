@@ -195,13 +195,14 @@ def test_proj_fwd_column_slices_of_gathered_matrix(avc, cuda_dev):
     assert rel_err(y1, ref) <= 2e-5
 
 
-@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("cta_group,mt", [("1", "1"), ("2", "1"), ("2", "2")])
 @pytest.mark.parametrize("workers", ["3", "5"])
-def test_gemm_multi_round_schedule_with_tail_split(avc, cuda_dev, monkeypatch, cta_group, workers):
-    """Persistent schedule with several rounds per worker and a partial last round (cut into sub-tiles), for
-    both the single-CTA and the CTA-pair kernels, forward (TN, bf16 + fp32 out) and dW (NT)."""
+def test_gemm_multi_round_schedule_with_tail_split(avc, cuda_dev, monkeypatch, cta_group, mt, workers):
+    """Persistent schedule with several rounds per worker and a partial last round (cut into sub-tiles), for the
+    single-CTA kernel and the CTA-pair kernel with 256- and 512-row tiles, forward (TN, bf16 + fp32 out) and dW (NT)."""
     L = avc._lib
     monkeypatch.setenv("AVC_GEMM_CTA_GROUP", cta_group)
+    monkeypatch.setenv("AVC_GEMM_MT", mt)  # 256- and 512-row pair tiles, for both GEMM modes
     monkeypatch.setenv("AVC_GEMM_MAX_WORKERS", workers)
     g = torch.Generator().manual_seed(77)
     B, R, K, N = 2, 300, 136, 1000
