@@ -129,6 +129,7 @@ class ConnectorStep:
         self.comm_reserve_sms = int(os.environ.get("AVC_COMM_RESERVE_SMS", "48"))
         self._comm_stream = None
         self._side_stream = None
+        self.prescale_grads = os.environ.get("AVC_PRESCALE_GRADS", "1") != "0"
         # run the small HBM-bound kernels of the fused step (text rows + masks, bias sums) on a side stream,
         # concurrently with the GEMMs
         self.side_streams = os.environ.get("AVC_SIDE_STREAMS", "1") != "0"
@@ -220,6 +221,11 @@ class ConnectorStep:
     def backward(self, allreduce: bool = True):
         g = self.bucket
         B, N, P = self.shape.batch, self.N, self.shape.prompt_len
+        # data parallel: the 1 / world factor of the gradient mean is folded into the dW / bias-sum epilogues, so the
+        # collective is a plain SUM (NVLS-capable) instead of AVG
+        inv = 1.0 / g.world_size() if (allreduce and self.prescale_grads) else 1.0
+        ga, gv = self.sa * inv, self.sv * inv
+        pre = inv != 1.0
         dba = g["audio_connector.linear.bias"] if self.use_a else None
         dbv = g["video_connector.linear.bias"] if self.use_v else None
         if self.direct:
@@ -237,21 +243,21 @@ class ConnectorStep:
         cs_done = None
         if self.side_streams and self.direct:
             # the bias column sums only read d(inputs_embeds): run them under the dW GEMM
-            cs_done = self._on_side("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa,
-                                                               alpha1=self.sv, **cs))
+            cs_done = self._on_side("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv,
+                                                               **cs))
         if not overlap:
             xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
             dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
                   ([g["video_connector.linear.weight"]] if self.use_v else [])
-            al = ([self.sa] if self.use_a else []) + ([self.sv] if self.use_v else [])
+            al = ([ga] if self.use_a else []) + ([gv] if self.use_v else [])
             self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, xs, dws, al, dy_row_base=base))
             if cs_done is not None:
                 torch.cuda.current_stream().wait_event(cs_done)
             else:
-                self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv,
+                self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv,
                                                        **cs))
             if allreduce:
-                g.allreduce()
+                g.allreduce(prescaled=pre)
             return g
         # Data-parallel overlap: the audio weight gradient (2/3 of the bucket at cfg2) is all-reduced on a side stream
         # while the video weight gradient and the bias sums are still being computed on `comm_reserve_sms` fewer SMs;
@@ -260,25 +266,25 @@ class ConnectorStep:
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=self.device)
         comm = self._comm_stream
-        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, [xa], [g["audio_connector.linear.weight"]], [self.sa],
+        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, [xa], [g["audio_connector.linear.weight"]], [ga],
                                                          dy_row_base=base))
         e1 = torch.cuda.Event()
         e1.record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(e1)
-            g.allreduce_span("audio_connector.linear.weight", "audio_connector.linear.weight")
+            g.allreduce_span("audio_connector.linear.weight", "audio_connector.linear.weight", prescaled=pre)
         sms = self._num_sms - self.comm_reserve_sms
-        self._timed("proj_bwd_dw_v", lambda: L.proj_bwd_dw(dy, [xv], [g["video_connector.linear.weight"]], [self.sv],
+        self._timed("proj_bwd_dw_v", lambda: L.proj_bwd_dw(dy, [xv], [g["video_connector.linear.weight"]], [gv],
                                                            dy_row_base=base, max_sms=sms))
         if cs_done is not None:
             main.wait_event(cs_done)
         else:
-            self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=self.sa, alpha1=self.sv, **cs))
+            self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, **cs))
         e2 = torch.cuda.Event()
         e2.record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(e2)
-            g.allreduce_span("video_connector.linear.weight", "video_connector.linear.bias")
+            g.allreduce_span("video_connector.linear.weight", "video_connector.linear.bias", prescaled=pre)
             e3 = torch.cuda.Event()
             e3.record(comm)
         main.wait_event(e3)

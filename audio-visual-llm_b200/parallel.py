@@ -51,15 +51,21 @@ class GradBucket:
             return 1
         return dist.get_world_size(self.group)
 
-    def allreduce(self, async_op: bool = False):
-        """flat <- mean over ranks.  No-op for a single process."""
+    def allreduce(self, async_op: bool = False, prescaled: bool = False):
+        """flat <- mean over ranks.  No-op for a single process.
+
+        prescaled=True: the producer already divided its gradients by the world size (the dW GEMM / bias-sum
+        epilogues take the factor for free), so a plain SUM is issued -- which, unlike AVG, lets NCCL use the
+        in-switch NVLS reduction on NVSwitch systems."""
         ws = self.world_size()
         if ws == 1:
             return None
         if dist.get_backend(self.group) == "nccl":
-            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+            op = dist.ReduceOp.SUM if prescaled else dist.ReduceOp.AVG
+            return dist.all_reduce(self.flat, op=op, group=self.group, async_op=async_op)
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=False)  # gloo (CPU tests)
-        self.flat.div_(ws)
+        if not prescaled:
+            self.flat.div_(ws)
         return work
 
     def span(self, first: str, last: str) -> torch.Tensor:
@@ -70,7 +76,7 @@ class GradBucket:
         hi = self.views[names[j]].data_ptr() - self.flat.data_ptr() + self.views[names[j]].numel() * 4
         return self.flat[lo // 4: hi // 4]
 
-    def allreduce_span(self, first: str, last: str):
+    def allreduce_span(self, first: str, last: str, prescaled: bool = False):
         """Average only views `first` .. `last`; used to overlap the reduction of finished gradients with the
         kernels that still produce the rest."""
         ws = self.world_size()
@@ -78,10 +84,11 @@ class GradBucket:
             return
         t = self.span(first, last)
         if dist.get_backend(self.group) == "nccl":
-            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if prescaled else dist.ReduceOp.AVG, group=self.group)
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-            t.div_(ws)
+            if not prescaled:
+                t.div_(ws)
 
     def attach(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]]) -> None:
         """Point each parameter's .grad at its bucket view (so optimizers / clip_grad_norm_ see the reduced grads)."""
