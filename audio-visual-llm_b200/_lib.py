@@ -20,6 +20,8 @@ EXPORTS = (
     "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",
     "avc_splice_bwd", "avc_row_resample", "avc_sumsq_workspace_bytes", "avc_sumsq", "avc_adamw_step",
     "avc_gelu_fwd", "avc_gelu_bwd", "avc_pack_weight_t",
+    "avc_comm_flag_bytes", "avc_comm_alloc", "avc_comm_free", "avc_comm_export", "avc_comm_open", "avc_comm_close",
+    "avc_proj_bwd_dw_allreduce", "avc_comm_signal_extra",
 )
 
 
@@ -49,6 +51,17 @@ class AvcSplice(C.Structure):
     ]
 
 
+COMM_MAX_WORLD = 8
+
+
+class AvcComm(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
+        ("bucket", C.c_void_p * COMM_MAX_WORLD), ("flags", C.c_void_p * COMM_MAX_WORLD), ("status", C.c_void_p),
+        ("timeout_ns", C.c_uint64), ("bucket_bytes", C.c_uint64),
+    ]
+
+
 class ConnectorError(RuntimeError):
     """Raised for every non-zero status of the C ABI (message from avc_last_error())."""
 
@@ -71,6 +84,12 @@ def load() -> C.CDLL:
     lib.avc_last_error.restype = C.c_char_p
     lib.avc_colsum_workspace_bytes.restype = C.c_size_t
     lib.avc_colsum_workspace_bytes.argtypes = [C.c_int32]
+    lib.avc_comm_flag_bytes.restype = C.c_size_t
+    lib.avc_comm_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.avc_comm_free.argtypes = [C.c_void_p]
+    lib.avc_comm_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.avc_comm_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.avc_comm_close.argtypes = [C.c_void_p]
     if lib.avc_abi_version() != AVC_ABI_VERSION:
         raise ConnectorError(f"ABI version mismatch: library {lib.avc_abi_version()} != binding {AVC_ABI_VERSION}")
     _lib = lib
@@ -152,6 +171,70 @@ def proj_bwd_dw(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Seque
     check(load().avc_proj_bwd_dw(
         C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
         _mat_array([mat(t) for t in dw_segs]), al, C.c_int32(max_sms), stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------ peer memory (data parallel)
+class _DeviceBlock:
+    """A raw device allocation exposed through __cuda_array_interface__ so torch can alias it without a copy."""
+
+    def __init__(self, ptr: int, numel: int, typestr: str):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def comm_alloc(nbytes: int) -> int:
+    """Zero-filled cudaMalloc block on the current device that other processes can map (CUDA IPC)."""
+    p = C.c_void_p()
+    check(load().avc_comm_alloc(C.c_size_t(nbytes), C.byref(p)))
+    return int(p.value)
+
+
+def comm_free(ptr: int) -> None:
+    check(load().avc_comm_free(C.c_void_p(ptr)))
+
+
+def comm_export(ptr: int) -> bytes:
+    h = C.create_string_buffer(64)
+    check(load().avc_comm_export(C.c_void_p(ptr), h))
+    return h.raw
+
+
+def comm_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    h = C.create_string_buffer(handle, 64)
+    check(load().avc_comm_open(h, C.byref(p)))
+    return int(p.value)
+
+
+def comm_close(ptr: int) -> None:
+    check(load().avc_comm_close(C.c_void_p(ptr)))
+
+
+def comm_flag_bytes() -> int:
+    return int(load().avc_comm_flag_bytes())
+
+
+def as_tensor(ptr: int, numel: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """torch view of `numel` elements at device address `ptr` (no copy; the caller keeps the block alive)."""
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DeviceBlock(ptr, numel, typestr), device=device)
+
+
+def proj_bwd_dw_allreduce(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
+                          alpha: Sequence[float], comm: AvcComm, extra0: Optional[torch.Tensor] = None,
+                          extra1: Optional[torch.Tensor] = None, dy_row_base: int = 0, max_sms: int = 0) -> None:
+    """proj_bwd_dw whose launch also all-reduces (sums) the dW segments and the extra ranges over the ranks."""
+    al = (C.c_float * len(x_segs))(*alpha)
+    check(load().avc_proj_bwd_dw_allreduce(
+        C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
+        _mat_array([mat(t) for t in dw_segs]), al, C.byref(comm), C.c_void_p(_ptr(extra0)),
+        C.c_int64(0 if extra0 is None else extra0.numel()), C.c_void_p(_ptr(extra1)),
+        C.c_int64(0 if extra1 is None else extra1.numel()), C.c_int32(max_sms), stream_ptr()))
+
+
+def comm_signal_extra(comm: AvcComm, extra0_len: int, extra1_len: int) -> None:
+    check(load().avc_comm_signal_extra(C.byref(comm), C.c_int64(extra0_len), C.c_int64(extra1_len), stream_ptr()))
 
 
 def colsum_workspace(cols: int, device) -> torch.Tensor:

@@ -1,6 +1,6 @@
 // C ABI of the B200-native clip_whisper connector (include/avconnector_b200.h).
 // Validates arguments, builds TMA tensor maps, and enqueues the sm_100a kernels on the caller's
-// stream.  Nothing here allocates device memory, synchronises, or falls back to the CPU.
+// stream.  Nothing here falls back to the CPU; only the avc_comm_* peer-memory helpers allocate or synchronise.
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -252,8 +252,49 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   return AVC_OK;
 }
 
-int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
-                    const float* alpha, int32_t max_sms, void* stream) {
+// avc_comm -> kernel arguments (pointer / range validation; offsets are relative to the local bucket)
+static int fill_comm(const avc_comm* c, const float* extra0, int64_t extra0_len, const float* extra1,
+                     int64_t extra1_len, avc::CommArgs* out) {
+  if (c == nullptr) return fail(AVC_ERR_INVALID, "comm: null descriptor");
+  if (c->world < 1 || c->world > avc::COMM_MAX_WORLD || c->rank < 0 || c->rank >= c->world)
+    return fail(AVC_ERR_INVALID, "comm: world %d / rank %d out of range (1..%d)", c->world, c->rank,
+                avc::COMM_MAX_WORLD);
+  if (c->epoch == 0) return fail(AVC_ERR_INVALID, "comm: epochs count from 1");
+  if (c->status == nullptr) return fail(AVC_ERR_INVALID, "comm: null status word");
+  if (c->bucket_bytes == 0 || c->bucket_bytes % 16 != 0)
+    return fail(AVC_ERR_INVALID, "comm: bucket_bytes must be a positive multiple of 16");
+  memset(out, 0, sizeof(*out));
+  out->world = c->world;
+  out->rank = c->rank;
+  out->epoch = c->epoch;
+  for (int p = 0; p < c->world; ++p) {
+    if (c->bucket[p] == nullptr || c->flags[p] == nullptr)
+      return fail(AVC_ERR_INVALID, "comm: rank %d's bucket / flag area is not mapped", p);
+    if ((reinterpret_cast<uintptr_t>(c->bucket[p]) & 15) || (reinterpret_cast<uintptr_t>(c->flags[p]) & 15))
+      return fail(AVC_ERR_INVALID, "comm: bucket / flag pointers must be 16-byte aligned");
+    out->data[p] = static_cast<float*>(c->bucket[p]);
+    out->flags[p] = static_cast<uint32_t*>(c->flags[p]);
+  }
+  const float* ex[2] = {extra0, extra1};
+  const int64_t len[2] = {extra0_len, extra1_len};
+  for (int k = 0; k < 2; ++k) {
+    if (ex[k] == nullptr || len[k] == 0) continue;
+    const int64_t off = ex[k] - static_cast<const float*>(c->bucket[c->rank]);
+    if (off < 0 || off % 4 != 0 || len[k] < 0 || len[k] % 4 != 0 || len[k] > (1 << 30) ||
+        static_cast<uint64_t>(off + len[k]) * 4 > c->bucket_bytes)
+      return fail(AVC_ERR_INVALID, "comm: extra range %d must start inside the local bucket, 16-byte aligned, and "
+                  "hold a multiple of 4 floats", k);
+    out->extra_off[k] = off;
+    out->extra_len[k] = static_cast<int>(len[k]);
+  }
+  out->status = c->status;
+  out->timeout_ns = c->timeout_ns != 0 ? c->timeout_ns : 20000000000ull;
+  return AVC_OK;
+}
+
+static int proj_bwd_dw_impl(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
+                            const float* alpha, const avc::CommArgs* comm, uint64_t bucket_bytes, int32_t max_sms,
+                            void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (max_sms < 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: negative max_sms");
@@ -299,8 +340,109 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
   g.red_kblocks_per_batch = static_cast<int>(ceil_div(red_rows, avc::GEMM_BK));
   g.a_row_base = dy_row_base;
   g.d_rows = static_cast<int>(H);
+  if (comm != nullptr) {
+    if (cg != 2) return fail(AVC_ERR_UNSUPPORTED, "proj_bwd_dw_allreduce needs the CTA-pair GEMM (AVC_GEMM_CTA_GROUP=2)");
+    g.comm = *comm;
+    for (int s = 0; s < nseg; ++s) {
+      // every rank addresses tile (row, col) of segment s at the same offset of its bucket
+      if (dw[s].row_stride != dw[s].cols)
+        return fail(AVC_ERR_INVALID, "proj_bwd_dw_allreduce: dW segment %d must be contiguous", s);
+      const int64_t off = static_cast<const float*>(dw[s].ptr) - comm->data[comm->rank];
+      if (off < 0 || off % 4 != 0 || static_cast<uint64_t>(off + dw[s].rows * dw[s].cols) * 4 > bucket_bytes)
+        return fail(AVC_ERR_INVALID, "proj_bwd_dw_allreduce: dW segment %d is not inside the local bucket", s);
+      g.comm.seg_off[s] = off;
+    }
+    const int items = avc::gemm_work_items(g, cg, di.num_sms);
+    if (items > avc::COMM_MAX_ITEMS)
+      return fail(AVC_ERR_UNSUPPORTED, "proj_bwd_dw_allreduce: %d work items exceed the flag area (%d)", items,
+                  avc::COMM_MAX_ITEMS);
+  }
   cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, cg, mt, di.num_sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_bwd_dw launch");
+  return AVC_OK;
+}
+
+int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
+                    const float* alpha, int32_t max_sms, void* stream) {
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, nullptr, 0, max_sms, stream);
+}
+
+int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
+                              const avc_mat* dw, const float* alpha, const avc_comm* comm, const float* extra0,
+                              int64_t extra0_len, const float* extra1, int64_t extra1_len, int32_t max_sms,
+                              void* stream) {
+  avc::CommArgs c;
+  if (int rc = fill_comm(comm, extra0, extra0_len, extra1, extra1_len, &c)) return rc;
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, &c, comm->bucket_bytes, max_sms, stream);
+}
+
+int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extra1_len, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  avc::CommArgs c;
+  // only the lengths matter here (which ranks own a chunk); offsets are not dereferenced
+  if (int rc = fill_comm(comm, nullptr, 0, nullptr, 0, &c)) return rc;
+  if (extra0_len < 0 || extra1_len < 0 || extra0_len > (1 << 30) || extra1_len > (1 << 30))
+    return fail(AVC_ERR_INVALID, "comm_signal_extra: bad range length");
+  c.extra_len[0] = static_cast<int>(extra0_len);
+  c.extra_len[1] = static_cast<int>(extra1_len);
+  cudaError_t e = avc::launch_comm_signal_extra(c, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "comm_signal_extra launch");
+  return AVC_OK;
+}
+
+size_t avc_comm_flag_bytes(void) { return static_cast<size_t>(avc::COMM_FLAG_WORDS) * 4; }
+
+int avc_comm_alloc(size_t bytes, void** ptr) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (ptr == nullptr || bytes == 0) return fail(AVC_ERR_INVALID, "comm_alloc: bad argument");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "comm_alloc cudaMalloc");
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e, "comm_alloc cudaMemset");
+  }
+  *ptr = p;
+  return AVC_OK;
+}
+
+int avc_comm_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "comm_free");
+  return AVC_OK;
+}
+
+int avc_comm_export(const void* ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+  if (ptr == nullptr || handle64 == nullptr) return fail(AVC_ERR_INVALID, "comm_export: null pointer");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+  memcpy(handle64, &h, sizeof(h));
+  return AVC_OK;
+}
+
+int avc_comm_open(const void* handle64, void** ptr) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (ptr == nullptr || handle64 == nullptr) return fail(AVC_ERR_INVALID, "comm_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  // maps the exporting process's allocation and enables peer access from the current device to its GPU
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+  *ptr = p;
+  return AVC_OK;
+}
+
+int avc_comm_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
   return AVC_OK;
 }
 

@@ -16,6 +16,36 @@ enum GemmMode : int {
   GEMM_NT = 1,  // D[m,n] = sum_r A[r,m] * B[r,n]      (both operands MN-major)  -> dW = dY^T * X
 };
 
+// ------------------------------------------------------------------ fused dW GEMM + gradient all-reduce over peer memory
+// Data-parallel training: every rank's dW GEMM writes its partial weight gradient into its own copy of the flat
+// gradient bucket; the buckets of all ranks are mapped into every process (CUDA IPC over NVLink).  Work item w of the
+// persistent GEMM schedule (a tile or tail sub-tile, the same list on every rank) is owned by rank w % world.  Extra
+// "comm" warps of the GEMM CTAs wait until all ranks have flagged item w, sum the `world` partial tiles in rank
+// order with peer loads and store the result into every rank's bucket with peer stores -- while the tensor cores
+// work on later tiles.  Flags are epoch numbers (one epoch per launch), so nothing is reset between steps.
+constexpr int COMM_MAX_WORLD = 8;
+constexpr int COMM_MAX_ITEMS = 2048;                       // work items per launch the flag area has room for
+constexpr int COMM_ITEM_FLAGS = 0;                         // [item][src rank] epoch: src's partial of item is in its bucket
+constexpr int COMM_EXTRA_FLAGS = COMM_MAX_ITEMS * COMM_MAX_WORLD;          // [src rank]: src's extra ranges (bias sums) are ready
+constexpr int COMM_DONE_FLAGS = COMM_EXTRA_FLAGS + COMM_MAX_WORLD;         // [src rank]: src has broadcast everything it owns
+constexpr int COMM_ITEM_COUNT = COMM_DONE_FLAGS + COMM_MAX_WORLD;          // local: epilogue-warp arrivals per item
+constexpr int COMM_DONE_COUNT = COMM_ITEM_COUNT + COMM_MAX_ITEMS;          // local: comm warps that have finished
+constexpr int COMM_FLAG_WORDS = COMM_DONE_COUNT + 32;
+constexpr int COMM_ERR_TIMEOUT = 1;
+
+struct CommArgs {
+  int world;                        // 0: plain GEMM (no comm warps)
+  int rank;
+  uint32_t epoch;                   // same strictly increasing number on every rank, one per launch
+  float* data[COMM_MAX_WORLD];      // gradient bucket of every rank as mapped in this process (data[rank] is local)
+  uint32_t* flags[COMM_MAX_WORLD];  // flag area (COMM_FLAG_WORDS words) of every rank
+  int64_t seg_off[2];               // float offset of output segment s (dW_s, row-major, ld = d_cols[s]) in the bucket
+  int64_t extra_off[2];             // up to two flat float ranges reduced as well once every rank flagged them
+  int extra_len[2];                 //   (the bias gradients; multiples of 4 floats, 16-byte aligned)
+  int32_t* status;                  // local device word: COMM_ERR_* on failure
+  uint64_t timeout_ns;              // give up (status = timeout) instead of hanging when a peer never shows up
+};
+
 struct GemmArgs {
   CUtensorMap ma[2];  // TN: A operand per K segment.        NT: ma[0] = dY  ([batch][rows][m])
   CUtensorMap mb[2];  // TN: B operand (weights) per K seg.  NT: X per output segment ([batch][rows][n])
@@ -51,6 +81,7 @@ struct GemmArgs {
   float alpha[2];            // NT: output scale per segment
   float bias_scale[2];       // TN: bias multipliers (fusion_scale folded into the bias)
   int act;                   // 0 = identity, 1 = GELU (erf form)
+  CommArgs comm;             // NT only: world >= 1 fuses the gradient all-reduce into the launch (0: plain GEMM)
 };
 
 // N tile that minimises (waves x per-tile time) for `m_blocks` x ceil(n_s / bn) tiles on `num_sms` persistent CTAs.
@@ -64,6 +95,10 @@ int gemm_m_subtiles(int cta_group, GemmMode mode);
 // m_subtiles * GEMM_BM rows of A and bn / cta_group rows of B
 cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int m_subtiles,
                         int num_sms, cudaStream_t stream);
+// work items (tiles + tail sub-tiles) the launch above will schedule; the fused all-reduce needs <= COMM_MAX_ITEMS
+int gemm_work_items(const GemmArgs& args, int cta_group, int num_sms);
+// flags every owner that this rank's extra ranges (bias gradients) hold their partial sums for `epoch`
+cudaError_t launch_comm_signal_extra(const CommArgs& comm, cudaStream_t stream);
 
 // ------------------------------------------------------------------ gather (align + stack + concat)
 struct GatherArgs {

@@ -35,7 +35,9 @@ constexpr int EPI_WARPS = 4;
 constexpr int EPI_BUF_BYTES = 32 * 128;                   // 32 rows x 128 B per warp per buffer
 constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KB
 constexpr int BAR_BYTES = 256;
-constexpr int kThreads = 32 * (2 + EPI_WARPS);
+constexpr int COMM_WARPS = 4;      // fused all-reduce: warps that move finished gradient tiles between the GPUs
+constexpr int COMM_UNIT_ROWS = 8;  // rows of a tile one comm warp reduces per step of its work list
+constexpr int threads_for(bool comm) { return 32 * (2 + EPI_WARPS + (comm ? COMM_WARPS : 0)); }
 constexpr int MN_ATOM_BYTES = BK * 128;  // one 64-wide MN-major atom column: BK rows x 128 B
 constexpr int kMaxStages = 6;
 
@@ -63,8 +65,78 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int MODE, bool OUT_F32, int CG, int MT>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
+// ---------------------------------------------------------------------------------- fused all-reduce (comm warps)
+// Wait until every rank's flag word f[0 .. world) has reached this launch's epoch.  Bounded: a peer that never shows
+// up sets the status word (the host raises) instead of hanging the box.
+__device__ __forceinline__ bool comm_wait(const uint32_t* f, const CommArgs& cm, int lane) {
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  for (;;) {
+    const uint32_t v = lane < cm.world ? ld_acquire_sys(f + lane) : cm.epoch;
+    if (__all_sync(0xffffffffu, static_cast<int32_t>(v - cm.epoch) >= 0)) return true;
+    __nanosleep(128);
+    if ((++spins & 0x7fu) == 0) {
+      int bail = 0;
+      if (lane == 0) {
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > cm.timeout_ns || *reinterpret_cast<volatile int32_t*>(cm.status) != 0) {
+          atomicCAS(cm.status, 0, COMM_ERR_TIMEOUT);
+          bail = 1;
+        }
+      }
+      if (__shfl_sync(0xffffffffu, bail, 0)) return false;
+    }
+  }
+}
+
+// out[p][base + r * ld + 4 c] (every rank p) = sum over ranks q (in rank order) of in[q][same] for r < rows,
+// c < nvec: 16 / W peer loads of 16 bytes in flight per lane, then the adds, then W peer stores.
+template <int W, bool RUNTIME_WORLD>
+__device__ __forceinline__ void comm_reduce_rows(const CommArgs& cm, int64_t base, int ld, int rows, int nvec,
+                                                 int lane) {
+  constexpr int C = 16 / W;
+  const int total = rows * nvec;
+  const int world = RUNTIME_WORLD ? cm.world : W;
+  for (int v0 = 0; v0 < total; v0 += 32 * C) {
+    float4 x[C][W];
+    int64_t off[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int v = v0 + c * 32 + lane;
+      off[c] = -1;
+      if (v < total) {
+        const int r = v / nvec;
+        off[c] = base + static_cast<int64_t>(r) * ld + 4 * (v - r * nvec);
+#pragma unroll
+        for (int p = 0; p < W; ++p)
+          if (p < world) x[c][p] = ld_relaxed_sys_v4(cm.data[p] + off[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (off[c] < 0) continue;
+      float4 s = x[c][0];
+#pragma unroll
+      for (int p = 1; p < W; ++p)
+        if (p < world) { s.x += x[c][p].x; s.y += x[c][p].y; s.z += x[c][p].z; s.w += x[c][p].w; }
+#pragma unroll
+      for (int p = 0; p < W; ++p)
+        if (p < world) st_relaxed_sys_v4(cm.data[p] + off[c], s);
+    }
+  }
+}
+
+// COMM template parameter of the kernel: 0 = plain GEMM; 1 / 2 / 4 / 8 = fused all-reduce specialised for that world
+// size; -1 = fused all-reduce for any world size <= COMM_MAX_WORLD (peer loops predicated at run time).
+template <int COMM>
+__device__ __forceinline__ void comm_reduce(const CommArgs& cm, int64_t base, int ld, int rows, int nvec, int lane) {
+  if constexpr (COMM > 0) comm_reduce_rows<COMM, false>(cm, base, ld, rows, nvec, lane);
+  else comm_reduce_rows<COMM_MAX_WORLD, true>(cm, base, ld, rows, nvec, lane);
+}
+
+template <int MODE, bool OUT_F32, int CG, int MT, int COMM>
+__global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
   using C = Cfg<CG, MT>;
   constexpr int kStages = C::kStages;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -263,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else {
+  } else if (COMM == 0 || warp < 2 + EPI_WARPS) {
     // ======================================================================= epilogue warps
     const int q = warp & 3;    // TMEM lane quarter this warp may access
     const int ew = warp - 2;   // staging buffer owner index
@@ -406,9 +478,87 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
+      if (COMM != 0) {
+        // This warp's part of work item w is in the local bucket once its TMA stores have completed.  The last of the
+        // item's EPI_WARPS x CG epilogue warps tells the item's owner rank that this rank's partial tile is ready.
+        if (lane == 0) {
+          const CommArgs& cm = args.comm;
+          bulk_wait_all<0>();
+          fence_proxy_async_all();
+          __threadfence_system();
+          uint32_t* lf = cm.flags[cm.rank];
+          if (atomicAdd(lf + COMM_ITEM_COUNT + w, 1u) == EPI_WARPS * CG - 1) {
+            atomicExch(lf + COMM_ITEM_COUNT + w, 0u);
+            __threadfence_system();
+            st_release_sys(cm.flags[w % cm.world] + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD + cm.rank, cm.epoch);
+          }
+        }
+        __syncwarp();
+      }
     }
     if (lane == 0 || (MODE == GEMM_TN && args.scatter_rows > 0)) bulk_wait_all<0>();
     __syncwarp();
+  } else if (COMM != 0) {
+    // ======================================================================= comm warps (fused gradient all-reduce)
+    const CommArgs& cm = args.comm;
+    const int g = static_cast<int>(blockIdx.x) * COMM_WARPS + (warp - 2 - EPI_WARPS);
+    const int G = static_cast<int>(gridDim.x) * COMM_WARPS;
+    uint32_t* lf = cm.flags[cm.rank];
+    constexpr int RG = TILE_M / COMM_UNIT_ROWS;  // row groups (units) per work item
+    const int n_owned = total_work > cm.rank ? (total_work - cm.rank + cm.world - 1) / cm.world : 0;
+    bool ok = true;
+    int cur = -1;
+    // units of the items this rank owns, in schedule order (= completion order), dealt round-robin to the comm warps
+    for (int u = g; ok && u < n_owned * RG; u += G) {
+      const int i = u / RG;
+      const int w = cm.rank + i * cm.world;
+      if (w != cur) {
+        ok = comm_wait(lf + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD, cm, lane);
+        cur = w;
+        if (!ok) break;
+      }
+      int m_blk, n_blk, n_off, width;
+      decode(w, m_blk, n_blk, n_off, width);
+      const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
+      const int ld = args.d_cols[seg];
+      const int col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off;
+      const int row0 = m_blk * TILE_M + (u - i * RG) * COMM_UNIT_ROWS;
+      const int rows = min(COMM_UNIT_ROWS, args.d_rows - row0);
+      const int cols = min(width, ld - col0);
+      if (rows <= 0 || cols <= 0) continue;
+      comm_reduce<COMM>(cm, cm.seg_off[seg] + static_cast<int64_t>(row0) * ld + col0, ld, rows, cols >> 2, lane);
+    }
+    // extra flat ranges (bias gradients, produced by another kernel): 128-float chunks, chunk e owned by rank
+    // e % world, the owner's chunks dealt to its comm warps from the back of the warp list
+    {
+      const int nch0 = (cm.extra_len[0] + 127) >> 7, nch1 = (cm.extra_len[1] + 127) >> 7;
+      bool waited = false;
+      for (int e = cm.rank; ok && e < nch0 + nch1; e += cm.world) {
+        if ((e / cm.world) % G != G - 1 - g) continue;
+        if (!waited) {
+          ok = comm_wait(lf + COMM_EXTRA_FLAGS, cm, lane);
+          waited = true;
+          if (!ok) break;
+        }
+        const int k = e >= nch0 ? 1 : 0;
+        const int ch = e - (k ? nch0 : 0);
+        comm_reduce<COMM>(cm, cm.extra_off[k] + 128 * ch, 0, 1, min(32, (cm.extra_len[k] - 128 * ch) >> 2), lane);
+      }
+    }
+    // This rank is done once all its comm warps are; the last one tells every rank and then waits until every rank
+    // has finished writing into this rank's bucket -- the launch does not complete before the bucket is final.
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence_system();
+      if (atomicAdd(lf + COMM_DONE_COUNT, 1u) == static_cast<uint32_t>(G - 1)) {
+        atomicExch(lf + COMM_DONE_COUNT, 0u);
+        __threadfence_system();
+        for (int p = 0; p < cm.world; ++p) st_release_sys(cm.flags[p] + COMM_DONE_FLAGS + cm.rank, cm.epoch);
+        last = 1;
+      }
+    }
+    if (__shfl_sync(0xffffffffu, last, 0)) comm_wait(lf + COMM_DONE_FLAGS, cm, lane);
   }
 
   tc_fence_before();
@@ -426,9 +576,9 @@ int env_int(const char* name, int dflt) {
   return e != nullptr ? atoi(e) : dflt;
 }
 
-template <int CG, int MT>
-cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
-  GemmArgs args = args_in;
+// Fills in the schedule fields of `args` (tail split, rasterisation, L2 hints); returns the worker count.
+template <int CG>
+int plan_schedule(GemmArgs& args, GemmMode mode, int num_sms) {
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
   int max_workers = num_sms / CG;
   const int cap = env_int("AVC_GEMM_MAX_WORKERS", 0);  // test knob: exercise multi-round schedules on small shapes
@@ -460,12 +610,21 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
       args.tail_split = best;
     }
   }
+  return workers;
+}
+
+template <int CG, int MT>
+cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
+  GemmArgs args = args_in;
+  const int workers = plan_schedule<CG>(args, mode, num_sms);
+  const bool comm = args.comm.world > 0;
+  if (comm && !(mode == GEMM_NT && out_fp32 && CG == 2)) return cudaErrorInvalidValue;
   auto run = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG, MT>::SMEM_ALLOC);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * CG);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads_for(comm));
     cfg.dynamicSmemBytes = Cfg<CG, MT>::SMEM_ALLOC;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -477,9 +636,28 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args);
   };
+  if constexpr (CG == 2) {
+    if (comm) {
+      switch (args.comm.world) {
+        case 1: return run(gemm_kernel<GEMM_NT, true, CG, MT, 1>);
+        case 2: return run(gemm_kernel<GEMM_NT, true, CG, MT, 2>);
+        case 4: return run(gemm_kernel<GEMM_NT, true, CG, MT, 4>);
+        case 8: return run(gemm_kernel<GEMM_NT, true, CG, MT, 8>);
+        default: return run(gemm_kernel<GEMM_NT, true, CG, MT, -1>);
+      }
+    }
+  }
   if (mode == GEMM_TN)
-    return out_fp32 ? run(gemm_kernel<GEMM_TN, true, CG, MT>) : run(gemm_kernel<GEMM_TN, false, CG, MT>);
-  return out_fp32 ? run(gemm_kernel<GEMM_NT, true, CG, MT>) : run(gemm_kernel<GEMM_NT, false, CG, MT>);
+    return out_fp32 ? run(gemm_kernel<GEMM_TN, true, CG, MT, 0>) : run(gemm_kernel<GEMM_TN, false, CG, MT, 0>);
+  return out_fp32 ? run(gemm_kernel<GEMM_NT, true, CG, MT, 0>) : run(gemm_kernel<GEMM_NT, false, CG, MT, 0>);
+}
+
+__global__ void comm_signal_extra_kernel(const __grid_constant__ CommArgs cm) {
+  // the kernel that produced the extra ranges ran before this one on the same stream
+  __threadfence_system();
+  const int nch = ((cm.extra_len[0] + 127) >> 7) + ((cm.extra_len[1] + 127) >> 7);
+  const int p = threadIdx.x;  // every rank that owns at least one chunk waits for this flag
+  if (p < cm.world && p < nch) st_release_sys(cm.flags[p] + COMM_EXTRA_FLAGS + cm.rank, cm.epoch);
 }
 
 }  // namespace
@@ -517,6 +695,19 @@ int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_worker
     if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+int gemm_work_items(const GemmArgs& args_in, int cta_group, int num_sms) {
+  GemmArgs args = args_in;
+  if (cta_group == 2) plan_schedule<2>(args, GEMM_NT, num_sms);
+  else plan_schedule<1>(args, GEMM_NT, num_sms);
+  const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+  return args.full_tiles + (num_tiles - args.full_tiles) * args.tail_split;
+}
+
+cudaError_t launch_comm_signal_extra(const CommArgs& comm, cudaStream_t stream) {
+  comm_signal_extra_kernel<<<1, 32, 0, stream>>>(comm);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int m_subtiles,

@@ -38,7 +38,7 @@ class StepShape:
 
 class ConnectorStep:
     def __init__(self, shape: StepShape, plan: FusePlan, device, out_dtype=torch.bfloat16, seed: int = 0,
-                 process_group=None, fuse_gather: bool = True):
+                 process_group=None, fuse_gather: bool = True, fused_allreduce: Optional[bool] = None):
         if out_dtype != torch.bfloat16:
             raise L.ConnectorError("the step engine runs the bf16 training configuration")
         L.require_device(torch.device(device).index or 0)
@@ -75,7 +75,15 @@ class ConnectorStep:
             sizes["audio_connector.linear.bias"] = (H,)
         if self.use_v:
             sizes["video_connector.linear.bias"] = (H,)
-        self.bucket = GradBucket(sizes, dev, process_group=process_group)
+        # Data parallel (N > 1): the gradient all-reduce runs INSIDE the dW GEMM launch over peer-mapped memory
+        # (`avc_proj_bwd_dw_allreduce`); AVC_FUSED_ALLREDUCE=0 falls back to one NCCL all-reduce after the backward.
+        import torch.distributed as dist
+        ddp = dist.is_available() and dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        if fused_allreduce is None:
+            fused_allreduce = ddp and dist.get_world_size(process_group) > 1 and \
+                os.environ.get("AVC_FUSED_ALLREDUCE", "1") != "0"
+        self.fused_allreduce = bool(fused_allreduce)
+        self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce)
         # ---- inputs resident in HBM
         self.audio = randn(s.batch, s.audio_frames, s.audio_dim).to(bf).to(dev) if self.use_a else None
         self.video = randn(s.batch, s.video_frames, s.video_dim).to(bf).to(dev) if self.use_v else None
@@ -239,6 +247,8 @@ class ConnectorStep:
             xa = self.A[:, :self.Ka] if self.use_a else None
             xv = self.A[:, self.Ka:] if self.use_v else None
             cs = dict(row_flags=self.flags)
+        if allreduce and self.fused_allreduce:
+            return self._backward_fused_allreduce(dy, base, xa, xv, dba, dbv, ga, gv, cs)
         overlap = allreduce and self.overlap_comm and g.world_size() > 1 and self.use_a and self.use_v
         cs_done = None
         if self.side_streams and self.direct:
@@ -288,6 +298,34 @@ class ConnectorStep:
             e3 = torch.cuda.Event()
             e3.record(comm)
         main.wait_event(e3)
+        return g
+
+    def _backward_fused_allreduce(self, dy, base, xa, xv, dba, dbv, ga, gv, cs):
+        """dW GEMM + all-reduce of the whole bucket in ONE launch.  The bias sums run first (on the side stream, under
+        the GEMM) and flag their ranges ready; the GEMM's comm warps reduce them together with the weight tiles."""
+        g = self.bucket
+        comm = g.peer.next_epoch()
+        H = self.shape.hidden
+        n0, n1 = (H if dba is not None else 0), (H if dbv is not None else 0)
+        ex = [t for t in (dba, dbv) if t is not None]
+
+        def bias_sums():
+            L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, **cs)
+            L.comm_signal_extra(comm, ex[0].numel(), ex[1].numel() if len(ex) > 1 else 0)
+
+        cs_done = None
+        if self.side_streams:
+            cs_done = self._on_side("colsum", bias_sums)
+        else:
+            self._timed("colsum", bias_sums)
+        xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
+        dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
+              ([g["video_connector.linear.weight"]] if self.use_v else [])
+        al = ([ga] if self.use_a else []) + ([gv] if self.use_v else [])
+        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw_allreduce(
+            dy, xs, dws, al, comm, extra0=ex[0], extra1=ex[1] if len(ex) > 1 else None, dy_row_base=base))
+        if cs_done is not None:
+            torch.cuda.current_stream().wait_event(cs_done)
         return g
 
     def step(self, allreduce: bool = True):

@@ -16,10 +16,93 @@ import torch
 import torch.distributed as dist
 
 
-class GradBucket:
-    """Flat fp32 gradient buffer with named views; `allreduce()` averages it over the process group."""
+class PeerMemory:
+    """This rank's gradient bucket + flag area in memory that every other rank's process maps (CUDA IPC, peer access
+    over NVLink), and the other ranks' blocks mapped here.  It is what `avc_proj_bwd_dw_allreduce` -- the dW GEMM with
+    the gradient all-reduce fused into the same kernel -- reads and writes; NCCL is not involved in that path.
+    Handles are exchanged once through the process group (`all_gather_object`).
 
-    def __init__(self, shapes: Dict[str, Tuple[int, ...]], device, process_group=None, align_elems: int = 64):
+    `next_epoch()` must be called once per fused launch, in the same order on every rank."""
+
+    def __init__(self, nfloats: int, device, process_group=None, timeout_s: float = 20.0):
+        from . import _lib as L
+
+        self._L = L
+        self.device = torch.device(device)
+        self.group = process_group
+        ddp = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if ddp else 1
+        self.rank = dist.get_rank(process_group) if ddp else 0
+        if self.world > L.COMM_MAX_WORLD:
+            raise L.ConnectorError(f"peer-memory all-reduce supports up to {L.COMM_MAX_WORLD} ranks, got {self.world}")
+        self.nfloats = nfloats
+        with torch.cuda.device(self.device):
+            self._own = (L.comm_alloc(nfloats * 4), L.comm_alloc(L.comm_flag_bytes()))
+            mine = (L.comm_export(self._own[0]), L.comm_export(self._own[1]))
+            handles = [mine]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, mine, group=process_group)
+            self.bucket_ptrs, self.flag_ptrs, self._opened = [], [], []
+            for r, (hb, hf) in enumerate(handles):
+                if r == self.rank:
+                    pb, pf = self._own
+                else:
+                    pb, pf = L.comm_open(hb), L.comm_open(hf)
+                    self._opened += [pb, pf]
+                self.bucket_ptrs.append(pb)
+                self.flag_ptrs.append(pf)
+        self.flat = L.as_tensor(self._own[0], nfloats, torch.float32, self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.timeout_ns = int(timeout_s * 1e9)
+        self.epoch = 0
+        if self.world > 1:
+            dist.barrier(group=process_group)  # every rank has mapped every block before the first launch
+
+    def next_epoch(self):
+        """Descriptor of the next fused launch (the epoch number is the protocol's only per-step state)."""
+        L = self._L
+        self.epoch += 1
+        c = L.AvcComm()
+        c.world, c.rank, c.epoch = self.world, self.rank, self.epoch
+        for r in range(self.world):
+            c.bucket[r] = self.bucket_ptrs[r]
+            c.flags[r] = self.flag_ptrs[r]
+        c.status = self.status.data_ptr()
+        c.timeout_ns = self.timeout_ns
+        c.bucket_bytes = self.nfloats * 4
+        return c
+
+    def check(self) -> None:
+        """Raise if a fused launch gave up waiting for a peer (synchronises)."""
+        code = int(self.status.item())
+        if code != 0:
+            raise self._L.ConnectorError(f"fused gradient all-reduce failed on rank {self.rank}: status {code} "
+                                         "(1 = a peer did not reach the same launch in time)")
+
+    def close(self) -> None:
+        L = self._L
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)  # nobody unmaps / frees while a peer may still touch the memory
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                L.comm_close(p)
+            self.flat = None
+            for p in self._own:
+                L.comm_free(p)
+        self._opened, self._own = [], None
+
+
+class GradBucket:
+    """Flat fp32 gradient buffer with named views; `allreduce()` averages it over the process group.
+
+    peer=True puts the buffer in `PeerMemory` so that the dW GEMM can all-reduce it itself (`self.peer`)."""
+
+    def __init__(self, shapes: Dict[str, Tuple[int, ...]], device, process_group=None, align_elems: int = 64,
+                 peer: bool = False):
         self.views: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         offs, total = {}, 0
         for name, shape in shapes.items():
@@ -28,7 +111,8 @@ class GradBucket:
                 n *= d
             offs[name] = (total, n, shape)
             total += (n + align_elems - 1) // align_elems * align_elems  # keep every view 256-byte aligned
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.peer: Optional[PeerMemory] = PeerMemory(total, device, process_group) if peer else None
+        self.flat = self.peer.flat if peer else torch.zeros(total, dtype=torch.float32, device=device)
         self._pads = []
         for name, (o, n, shape) in offs.items():
             self.views[name] = self.flat[o:o + n].view(*shape)

@@ -206,12 +206,14 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = eng.fused_tokens * world / (ms_per_step * 1e-3)
     assert int(eng.status.item()) == 0, "placeholder / token count mismatch"
+    if eng.bucket.peer is not None:
+        eng.bucket.peer.check()  # a fused all-reduce launch that gave up on a peer invalidates the run
 
     # the same step with the stand-alone gather and splice-bwd kernels (the general path: ragged lengths, CLS
     # views, explicit placeholder layouts); gives the per-kernel HBM numbers of the kernels the fused step skips
     unfused = None
     if rank == 0 and eng.direct:
-        eng2 = ConnectorStep(shape, plan, dev, seed=1234 + rank, fuse_gather=False)
+        eng2 = ConnectorStep(shape, plan, dev, seed=1234 + rank, fuse_gather=False, fused_allreduce=False)
         for _ in range(args.warmup):
             eng2.step(allreduce=False)
         torch.cuda.synchronize()
@@ -302,9 +304,12 @@ def main():
                    "parallelism": f"dp{world}", "step": ("fused: tower outputs -> 2-segment GEMM whose epilogue writes the AV rows of inputs_embeds -> text rows + masks; "
                                                         "dW GEMM and bias sums read d(inputs_embeds) in place"
                                                        if eng.direct else "gather -> GEMM -> splice; splice-bwd -> dW GEMM"),
-                   "collective": (("projector-grad all-reduce (NCCL avg, 100.7 MB fp32 flat bucket" +
-                                   ("; audio-weight span overlapped with the video-weight dW launch)" if eng.overlap_comm
-                                    else "; one call after the backward)")) if world > 1 else "none"),
+                   "collective": (("projector-grad all-reduce fused into the dW GEMM launch (100.7 MB fp32 flat bucket in "
+                                   "peer-mapped memory: comm warps of the GEMM CTAs sum finished tiles over NVLink "
+                                   "with peer loads / stores while later tiles are computed)") if eng.fused_allreduce
+                                  else ("projector-grad all-reduce (NCCL sum of pre-scaled grads, 100.7 MB fp32 flat bucket" +
+                                        ("; audio-weight span overlapped with the video-weight dW launch)" if eng.overlap_comm
+                                         else "; one call after the backward)"))) if world > 1 else "none"),
                    "l2": "no flush: one step streams ~0.9 GB (features, A, W, Y, embeds, grads) >> 126 MB L2"},
         "roofline": roofline, "kernels": kernels, "unfused_step": unfused, "cpu_baseline": cpu, "e2e": e2e,
         "clocks": clocks,

@@ -7,6 +7,7 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; nothing is allocated or freed
+ *     (except by the avc_comm_alloc / avc_comm_free peer-memory helpers)
  *   - feature / weight / embedding elements are bf16; masks, ids and labels are int64 (reference dtype)
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
  *   - return 0 on success, non-zero on error; avc_last_error() gives the message (thread-local)
@@ -100,6 +101,48 @@ AVC_API int avc_proj_bwd_dw(const avc_mat* dy /* bf16 [b][rows][H] */, int32_t d
                     const avc_mat* x /* [nseg] bf16 */, const avc_mat* dw /* [nseg] fp32 [H, K_s] */,
                     const float* alpha /* [nseg] */, int32_t max_sms /* 0 = all; < SM count leaves SMs free for a
                     concurrent collective (gradient all-reduce overlap) */, void* stream);
+
+/* ---- data parallel: the same weight-gradient GEMM with the gradient all-reduce fused into it ------------------
+ * One process per GPU; every rank keeps its projector gradients in ONE flat fp32 bucket allocated with
+ * avc_comm_alloc and mapped into every other rank's process (avc_comm_export / avc_comm_open: CUDA IPC, peer access
+ * over NVLink).  avc_proj_bwd_dw_allreduce computes this rank's dW tiles into its bucket exactly like
+ * avc_proj_bwd_dw and, IN THE SAME KERNEL, extra warps of the GEMM CTAs sum every finished tile over the ranks
+ * (peer loads, fixed rank order: deterministic and bit-identical on every rank) and store the sum into every rank's
+ * bucket (peer stores) while the tensor cores work on later tiles.  Up to two extra flat ranges of the bucket (the
+ * bias gradients, produced by avc_colsum on another stream) are reduced by the same launch once every rank has
+ * called avc_comm_signal_extra for this epoch.  When the launch completes the local bucket holds the SUM over ranks
+ * (fold 1 / world into alpha).  Every rank must issue the same sequence of calls with the same `epoch` (strictly
+ * increasing from 1).  The reference has no distributed code; the insertion point is between loss.backward() and
+ * clip_grad_norm_ (clip_whisper_trainer.py:454-458).
+ * A peer that does not show up within timeout_ns sets *status to 1 (and the kernel finishes) instead of hanging. */
+#define AVC_COMM_MAX_WORLD 8
+typedef struct avc_comm {
+  int32_t world;                     /* 1 .. AVC_COMM_MAX_WORLD */
+  int32_t rank;
+  uint32_t epoch;
+  uint32_t reserved;
+  void* bucket[AVC_COMM_MAX_WORLD];  /* base of every rank's gradient bucket as mapped in THIS process */
+  void* flags[AVC_COMM_MAX_WORLD];   /* every rank's flag area: avc_comm_flag_bytes() bytes from avc_comm_alloc */
+  int32_t* status;                   /* local device int32, zero-initialised */
+  uint64_t timeout_ns;               /* 0 = 20 s */
+  uint64_t bucket_bytes;             /* size of every rank's bucket (ranges passed to the calls are checked against it) */
+} avc_comm;
+AVC_API size_t avc_comm_flag_bytes(void);
+/* cudaMalloc + zero-fill on the current device (IPC-exportable, unlike pooled allocator blocks). */
+AVC_API int avc_comm_alloc(size_t bytes, void** ptr);
+AVC_API int avc_comm_free(void* ptr);
+/* 64-byte cudaIpcMemHandle_t of an avc_comm_alloc block, to be sent to the other ranks' processes ... */
+AVC_API int avc_comm_export(const void* ptr, void* handle64);
+/* ... which map it (enabling peer access from the current device) and unmap it again. */
+AVC_API int avc_comm_open(const void* handle64, void** ptr);
+AVC_API int avc_comm_close(void* ptr);
+/* dw[s].ptr, extra0, extra1 must lie inside comm->bucket[comm->rank]; dw[s] must be contiguous (row_stride == cols). */
+AVC_API int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
+                                      const avc_mat* dw, const float* alpha, const avc_comm* comm,
+                                      const float* extra0, int64_t extra0_len, const float* extra1,
+                                      int64_t extra1_len, int32_t max_sms, void* stream);
+/* Enqueue after the kernel that wrote this rank's extra ranges (same stream): flags them ready for comm->epoch. */
+AVC_API int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extra1_len, void* stream);
 
 /* ---- bias gradient: deterministic two-pass column sum over flagged rows -------------------------
  * out_i[c] = alpha_i * sum_{b, r < sum_rows : flag_i(b, r)} dY[b, dy_row_base + r, c]      (db = sum dY)
