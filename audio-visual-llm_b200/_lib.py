@@ -21,7 +21,7 @@ EXPORTS = (
     "avc_splice_bwd", "avc_row_resample", "avc_sumsq_workspace_bytes", "avc_sumsq", "avc_adamw_step",
     "avc_gelu_fwd", "avc_gelu_bwd", "avc_pack_weight_t",
     "avc_comm_flag_bytes", "avc_comm_alloc", "avc_comm_free", "avc_comm_export", "avc_comm_open", "avc_comm_close",
-    "avc_proj_bwd_dw_allreduce", "avc_comm_signal_extra",
+    "avc_proj_bwd_dw_allreduce", "avc_comm_signal_extra", "avc_colsum_comm", "avc_colsum_workspace_header_bytes",
 )
 
 
@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     lib.avc_last_error.restype = C.c_char_p
     lib.avc_colsum_workspace_bytes.restype = C.c_size_t
     lib.avc_colsum_workspace_bytes.argtypes = [C.c_int32]
+    lib.avc_colsum_workspace_header_bytes.restype = C.c_size_t
     lib.avc_comm_flag_bytes.restype = C.c_size_t
     lib.avc_comm_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.avc_comm_free.argtypes = [C.c_void_p]
@@ -238,19 +239,28 @@ def comm_signal_extra(comm: AvcComm, extra0_len: int, extra1_len: int) -> None:
 
 
 def colsum_workspace(cols: int, device) -> torch.Tensor:
-    n = load().avc_colsum_workspace_bytes(cols)
-    return torch.empty(n // 4, dtype=torch.float32, device=device)
+    """Scratch for `colsum`: partial sums behind a zero-initialised header of arrival counters (the kernel leaves the
+    header zero, so one workspace serves any number of stream-ordered calls)."""
+    lib = load()
+    ws = torch.empty(lib.avc_colsum_workspace_bytes(cols) // 4, dtype=torch.float32, device=device)
+    ws[: lib.avc_colsum_workspace_header_bytes() // 4].zero_()
+    return ws
 
 
 def colsum(dy: torch.Tensor, out0: Optional[torch.Tensor], out1: Optional[torch.Tensor], workspace: torch.Tensor,
            row_flags: Optional[torch.Tensor] = None, flag_rows0: int = 1 << 30, flag_rows1: int = 1 << 30,
-           alpha0: float = 1.0, alpha1: float = 1.0, dy_row_base: int = 0, sum_rows: Optional[int] = None) -> None:
+           alpha0: float = 1.0, alpha1: float = 1.0, dy_row_base: int = 0, sum_rows: Optional[int] = None,
+           comm: Optional[AvcComm] = None) -> None:
+    """comm: also flag out0 / out1 ready for that epoch's fused all-reduce (`proj_bwd_dw_allreduce` extras)."""
     m = mat(dy)
-    check(load().avc_colsum(
-        C.byref(m), C.c_int32(dy_row_base), C.c_int32(m.rows - dy_row_base if sum_rows is None else sum_rows),
-        C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
-        C.c_float(alpha0), C.c_float(alpha1), C.c_void_p(_ptr(out0)), C.c_void_p(_ptr(out1)),
-        C.c_void_p(workspace.data_ptr()), stream_ptr()))
+    args = (C.byref(m), C.c_int32(dy_row_base), C.c_int32(m.rows - dy_row_base if sum_rows is None else sum_rows),
+            C.c_void_p(_ptr(row_flags)), C.c_int32(flag_rows0), C.c_int32(flag_rows1),
+            C.c_float(alpha0), C.c_float(alpha1), C.c_void_p(_ptr(out0)), C.c_void_p(_ptr(out1)),
+            C.c_void_p(workspace.data_ptr()))
+    if comm is None:
+        check(load().avc_colsum(*args, stream_ptr()))
+    else:
+        check(load().avc_colsum_comm(*args, C.byref(comm), stream_ptr()))
 
 
 def pack_weight(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> None:

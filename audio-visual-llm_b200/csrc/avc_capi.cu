@@ -448,9 +448,11 @@ int avc_comm_close(void* ptr) {
 
 size_t avc_colsum_workspace_bytes(int32_t cols) { return avc::colsum_workspace_bytes(cols); }
 
-int avc_colsum(const avc_mat* dy, int32_t dy_row_base, int32_t sum_rows, const uint8_t* row_flags, int32_t flag_rows0,
-               int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1, void* workspace,
-               void* stream) {
+size_t avc_colsum_workspace_header_bytes(void) { return avc::colsum_workspace_header_bytes(); }
+
+static int colsum_impl(const avc_mat* dy, int32_t dy_row_base, int32_t sum_rows, const uint8_t* row_flags,
+                       int32_t flag_rows0, int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1,
+                       void* workspace, const avc_comm* comm, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (dy == nullptr || dy->ptr == nullptr) return fail(AVC_ERR_INVALID, "colsum: null dY");
@@ -475,9 +477,34 @@ int avc_colsum(const avc_mat* dy, int32_t dy_row_base, int32_t sum_rows, const u
   c.out0 = out0;
   c.out1 = out1;
   c.workspace = static_cast<float*>(workspace);
+  if (comm != nullptr) {
+    avc::CommArgs k;
+    if (int rc = fill_comm(comm, out0, out0 ? dy->cols : 0, out1, out1 ? dy->cols : 0, &k)) return rc;
+    // the ranks that own a 128-float chunk of the extra ranges wait for this flag (chunk e belongs to rank e % world)
+    const int nch = ((k.extra_len[0] + 127) >> 7) + ((k.extra_len[1] + 127) >> 7);
+    c.sig_owners = nch < k.world ? nch : k.world;
+    c.sig_rank = k.rank;
+    c.sig_epoch = k.epoch;
+    for (int p = 0; p < k.world; ++p) c.sig_flags[p] = k.flags[p];
+  }
   cudaError_t e = avc::launch_colsum(c, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "colsum launch");
   return AVC_OK;
+}
+
+int avc_colsum(const avc_mat* dy, int32_t dy_row_base, int32_t sum_rows, const uint8_t* row_flags, int32_t flag_rows0,
+               int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1, void* workspace,
+               void* stream) {
+  return colsum_impl(dy, dy_row_base, sum_rows, row_flags, flag_rows0, flag_rows1, alpha0, alpha1, out0, out1,
+                     workspace, nullptr, stream);
+}
+
+int avc_colsum_comm(const avc_mat* dy, int32_t dy_row_base, int32_t sum_rows, const uint8_t* row_flags,
+                    int32_t flag_rows0, int32_t flag_rows1, float alpha0, float alpha1, float* out0, float* out1,
+                    void* workspace, const avc_comm* comm, void* stream) {
+  if (comm == nullptr) return fail(AVC_ERR_INVALID, "colsum_comm: null comm descriptor");
+  return colsum_impl(dy, dy_row_base, sum_rows, row_flags, flag_rows0, flag_rows1, alpha0, alpha1, out0, out1,
+                     workspace, comm, stream);
 }
 
 int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows, int64_t cols,

@@ -166,9 +166,17 @@ struct ColsumArgs {
   float alpha0, alpha1;
   float* out0;               // [cols] may be null
   float* out1;               // [cols] may be null
-  float* workspace;          // colsum_workspace_bytes()
+  float* workspace;          // colsum_workspace_bytes(); the first colsum_workspace_header_bytes() are zero
+                             // before the first launch (the kernel leaves them zero)
+  // data parallel: when the sums are final, flag them ready for this epoch's fused all-reduce at the
+  // first sig_owners ranks (the ranks that own a chunk of the extra ranges); 0: no signal
+  int sig_owners;
+  int sig_rank;
+  uint32_t sig_epoch;
+  uint32_t* sig_flags[COMM_MAX_WORLD];
 };
 size_t colsum_workspace_bytes(int cols);
+size_t colsum_workspace_header_bytes();
 cudaError_t launch_colsum(const ColsumArgs& args, cudaStream_t stream);
 
 // Row resampling (sparse row mixing): out[b, i, :] = sum_t weight[t] * x[b, col[t], :], t in CSR row i.

@@ -32,7 +32,14 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 }
 
 constexpr int CS_THREADS = 256;
-constexpr int CS_MAX_CHUNKS = 296;
+constexpr int CS_MAX_CHUNKS = 296;   // row slabs (first-level partial sums)
+constexpr int CS_GROUP = 16;         // slabs per second-level group
+constexpr int CS_MAX_GROUPS = (CS_MAX_CHUNKS + CS_GROUP - 1) / CS_GROUP;
+constexpr int CS_MAX_COLGROUPS = 16;  // grid.y: 2048 columns each
+constexpr int CS_HEADER_WORDS = 1024;  // arrival counters (zero between launches), then the partial sums
+constexpr int CS_TOP_COUNT = CS_MAX_COLGROUPS * 32;  // [y][group] counters first, then [y], then one
+constexpr int CS_FINAL_COUNT = CS_TOP_COUNT + CS_MAX_COLGROUPS;
+static_assert(CS_MAX_GROUPS <= 32 && CS_FINAL_COUNT < CS_HEADER_WORDS, "colsum header layout");
 
 __device__ __forceinline__ void acc_bf16x8(float (&s)[8], const int4& v) {
   const uint32_t w[4] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y),
@@ -44,88 +51,120 @@ __device__ __forceinline__ void acc_bf16x8(float (&s)[8], const int4& v) {
   }
 }
 
-// partial[chunk][which][col]
-__global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(const __grid_constant__ ColsumArgs a,
-                                                                    int rows_per_chunk) {
-  const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows;
-  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * rows_per_chunk;
-  int64_t g1 = g0 + rows_per_chunk;
-  g1 = g1 < total_rows ? g1 : total_rows;
-  const int col = (blockIdx.y * CS_THREADS + threadIdx.x) * 8;
-  if (col >= a.cols) return;
-  float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  constexpr int U = 8;  // independent 16-byte loads in flight per thread
-  // (b, r) of the first row of this chunk; advanced incrementally (no per-row division)
-  int b = a.rows > 0 ? static_cast<int>(g0 / a.rows) : 0;
-  int r = static_cast<int>(g0 - static_cast<int64_t>(b) * a.rows);
-  const uint8_t* base = a.dy + static_cast<int64_t>(col) * 2;
-  for (int64_t gb = g0; gb < g1; gb += U) {
-    int4 v[U];
-    bool f0[U], f1[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      f0[u] = f1[u] = false;
-      v[u] = make_int4(0, 0, 0, 0);
-      if (gb + u < g1) {
-        if (a.row_flags != nullptr) {
-          const uint8_t fl = __ldg(a.row_flags + gb + u);
-          f0[u] = fl & 1; f1[u] = fl & 2;
-        } else {
-          f0[u] = r < a.flag_rows0; f1[u] = r < a.flag_rows1;
-        }
-        if (f0[u] || f1[u])
-          v[u] = ld_nc_v4(base + b * a.batch_stride + static_cast<int64_t>(r + a.row_base) * a.row_stride);
-        if (++r == a.rows) { r = 0; ++b; }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {  // fixed order: deterministic
-      if (f0[u]) acc_bf16x8(s0, v[u]);
-      if (f1[u]) acc_bf16x8(s1, v[u]);
-    }
-  }
-  float* p0 = a.workspace + (static_cast<int64_t>(blockIdx.x) * 2 + 0) * a.cols + col;
-  float* p1 = a.workspace + (static_cast<int64_t>(blockIdx.x) * 2 + 1) * a.cols + col;
-  *reinterpret_cast<float4*>(p0) = make_float4(s0[0], s0[1], s0[2], s0[3]);
-  *reinterpret_cast<float4*>(p0 + 4) = make_float4(s0[4], s0[5], s0[6], s0[7]);
-  *reinterpret_cast<float4*>(p1) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-  *reinterpret_cast<float4*>(p1 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+__device__ __forceinline__ void add8(float (&s)[8], const float* p) {
+  const float4 x = __ldcg(reinterpret_cast<const float4*>(p));
+  const float4 y = __ldcg(reinterpret_cast<const float4*>(p + 4));
+  s[0] += x.x; s[1] += x.y; s[2] += x.z; s[3] += x.w;
+  s[4] += y.x; s[5] += y.y; s[6] += y.z; s[7] += y.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&s)[8], float alpha) {
+  *reinterpret_cast<float4*>(p) = make_float4(alpha * s[0], alpha * s[1], alpha * s[2], alpha * s[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(alpha * s[4], alpha * s[5], alpha * s[6], alpha * s[7]);
 }
 
-// out[col] = alpha * sum over chunks, in a fixed order: 32 columns x 8 slices per CTA; slice s adds chunks
-// s, s+8, ... (independent loads in flight), then the 8 slice sums are added in order 0..7.
-__global__ void __launch_bounds__(CS_THREADS) colsum_final_kernel(const __grid_constant__ ColsumArgs a,
-                                                                  int nchunks) {
-  __shared__ float red[2][8][32];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane;
-  float s0 = 0.f, s1 = 0.f;
-  if (col < a.cols) {
-    int c = slice;
-    for (; c + 24 < nchunks; c += 32) {
-      float x0[4], x1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        x0[u] = a.workspace[(static_cast<int64_t>(c + 8 * u) * 2 + 0) * a.cols + col];
-        x1[u] = a.workspace[(static_cast<int64_t>(c + 8 * u) * 2 + 1) * a.cols + col];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { s0 += x0[u]; s1 += x1[u]; }
-    }
-    for (; c < nchunks; c += 8) {
-      s0 += a.workspace[(static_cast<int64_t>(c) * 2 + 0) * a.cols + col];
-      s1 += a.workspace[(static_cast<int64_t>(c) * 2 + 1) * a.cols + col];
+// `n` CTAs arrive on *counter; true (for every thread of the CTA) in the CTA that arrives last, which also puts the
+// counter back to zero for the next launch.  The CTA's global writes before the call are visible to the last CTA
+// after it.  Uses no shared memory (the kernel must fit next to a GEMM CTA that owns all of it).
+__device__ __forceinline__ bool cta_arrive_last(uint32_t* counter, uint32_t n) {
+  __threadfence();
+  __syncthreads();
+  int last = 0;
+  if (threadIdx.x == 0) {
+    if (atomicAdd(counter, 1u) == n - 1) {
+      atomicExch(counter, 0u);
+      last = 1;
     }
   }
-  red[0][slice][lane] = s0;
-  red[1][slice][lane] = s1;
-  __syncthreads();
-  if (slice == 0 && col < a.cols) {
-    float t0 = 0.f, t1 = 0.f;
+  last = __syncthreads_or(last);
+  if (last) __threadfence();
+  return last != 0;
+}
+
+// ONE launch, three levels, fixed summation order at every level (deterministic):
+//   1. CTA (slab, y) sums its rows for 2048 columns                       -> level-1 partial [slab][which][col]
+//   2. the last CTA of each group of 16 slabs adds the group's partials   -> level-2 partial [group][which][col]
+//   3. the last of those CTAs adds the <= 19 group sums, scales, writes out0 / out1
+//   4. (data parallel) the last of the grid.y finishing CTAs flags the sums ready for the fused all-reduce
+// No shared memory and 256 threads per CTA, so that the kernel runs next to the projector GEMM's CTAs.
+__global__ void __launch_bounds__(CS_THREADS, 4) colsum_kernel(const __grid_constant__ ColsumArgs a, int rows_per_chunk,
+                                                            int nchunks) {
+  const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows;
+  const int chunk = blockIdx.x, y = blockIdx.y;
+  const int64_t g0 = static_cast<int64_t>(chunk) * rows_per_chunk;
+  int64_t g1 = g0 + rows_per_chunk;
+  g1 = g1 < total_rows ? g1 : total_rows;
+  const int col = (y * CS_THREADS + threadIdx.x) * 8;
+  const bool active = col < a.cols;
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(a.workspace);
+  float* lvl2 = a.workspace + CS_HEADER_WORDS;
+  float* lvl1 = lvl2 + static_cast<int64_t>(CS_MAX_GROUPS) * 2 * a.cols;
+  if (active) {
+    float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    constexpr int U = 8;  // independent 16-byte loads in flight per thread
+    // (b, r) of the first row of this slab; advanced incrementally (no per-row division)
+    int b = a.rows > 0 ? static_cast<int>(g0 / a.rows) : 0;
+    int r = static_cast<int>(g0 - static_cast<int64_t>(b) * a.rows);
+    const uint8_t* base = a.dy + static_cast<int64_t>(col) * 2;
+    for (int64_t gb = g0; gb < g1; gb += U) {
+      int4 v[U];
+      bool f0[U], f1[U];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) { t0 += red[0][s][lane]; t1 += red[1][s][lane]; }
-    if (a.out0 != nullptr) a.out0[col] = a.alpha0 * t0;
-    if (a.out1 != nullptr) a.out1[col] = a.alpha1 * t1;
+      for (int u = 0; u < U; ++u) {
+        f0[u] = f1[u] = false;
+        v[u] = make_int4(0, 0, 0, 0);
+        if (gb + u < g1) {
+          if (a.row_flags != nullptr) {
+            const uint8_t fl = __ldg(a.row_flags + gb + u);
+            f0[u] = fl & 1; f1[u] = fl & 2;
+          } else {
+            f0[u] = r < a.flag_rows0; f1[u] = r < a.flag_rows1;
+          }
+          if (f0[u] || f1[u])
+            v[u] = ld_nc_v4(base + b * a.batch_stride + static_cast<int64_t>(r + a.row_base) * a.row_stride);
+          if (++r == a.rows) { r = 0; ++b; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // fixed order: deterministic
+        if (f0[u]) acc_bf16x8(s0, v[u]);
+        if (f1[u]) acc_bf16x8(s1, v[u]);
+      }
+    }
+    store8(lvl1 + (static_cast<int64_t>(chunk) * 2 + 0) * a.cols + col, s0, 1.f);
+    store8(lvl1 + (static_cast<int64_t>(chunk) * 2 + 1) * a.cols + col, s1, 1.f);
+  }
+  const int group = chunk / CS_GROUP;
+  const int ngroups = (nchunks + CS_GROUP - 1) / CS_GROUP;
+  const int c0 = group * CS_GROUP;
+  const int c1 = c0 + CS_GROUP < nchunks ? c0 + CS_GROUP : nchunks;
+  if (!cta_arrive_last(hdr + y * 32 + group, static_cast<uint32_t>(c1 - c0))) return;
+  if (active) {
+    float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) {
+      add8(s0, lvl1 + (static_cast<int64_t>(c) * 2 + 0) * a.cols + col);
+      add8(s1, lvl1 + (static_cast<int64_t>(c) * 2 + 1) * a.cols + col);
+    }
+    store8(lvl2 + (static_cast<int64_t>(group) * 2 + 0) * a.cols + col, s0, 1.f);
+    store8(lvl2 + (static_cast<int64_t>(group) * 2 + 1) * a.cols + col, s1, 1.f);
+  }
+  if (!cta_arrive_last(hdr + CS_TOP_COUNT + y, static_cast<uint32_t>(ngroups))) return;
+  if (active) {
+    float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int g = 0; g < ngroups; ++g) {
+      add8(s0, lvl2 + (static_cast<int64_t>(g) * 2 + 0) * a.cols + col);
+      add8(s1, lvl2 + (static_cast<int64_t>(g) * 2 + 1) * a.cols + col);
+    }
+    if (a.out0 != nullptr) store8(a.out0 + col, s0, a.alpha0);
+    if (a.out1 != nullptr) store8(a.out1 + col, s1, a.alpha1);
+  }
+  if (a.sig_owners <= 0) return;
+  __threadfence_system();
+  if (!cta_arrive_last(hdr + CS_FINAL_COUNT, gridDim.y)) return;
+  if (threadIdx.x < static_cast<unsigned>(a.sig_owners)) {
+    __threadfence_system();
+    st_release_sys(a.sig_flags[threadIdx.x] + COMM_EXTRA_FLAGS + a.sig_rank, a.sig_epoch);
   }
 }
 
@@ -394,13 +433,18 @@ cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int6
 }
 
 size_t colsum_workspace_bytes(int cols) {
-  return static_cast<size_t>(CS_MAX_CHUNKS) * 2 * static_cast<size_t>(cols) * sizeof(float);
+  return (static_cast<size_t>(CS_HEADER_WORDS) +
+          static_cast<size_t>(CS_MAX_CHUNKS + CS_MAX_GROUPS) * 2 * static_cast<size_t>(cols)) * sizeof(float);
 }
+size_t colsum_workspace_header_bytes() { return static_cast<size_t>(CS_HEADER_WORDS) * sizeof(float); }
 
 cudaError_t launch_colsum(const ColsumArgs& a, cudaStream_t stream) {
   if (a.cols <= 0) return cudaSuccess;
   if (a.cols % 8 != 0 || a.row_stride % 16 != 0 || a.batch_stride % 16 != 0 ||
-      (reinterpret_cast<uintptr_t>(a.dy) & 15) != 0 || a.workspace == nullptr)
+      (reinterpret_cast<uintptr_t>(a.dy) & 15) != 0 || a.workspace == nullptr ||
+      (reinterpret_cast<uintptr_t>(a.workspace) & 15) != 0 ||
+      (a.out0 != nullptr && (reinterpret_cast<uintptr_t>(a.out0) & 15) != 0) ||
+      (a.out1 != nullptr && (reinterpret_cast<uintptr_t>(a.out1) & 15) != 0))
     return cudaErrorMisalignedAddress;
   const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows;
   int nchunks = static_cast<int>(total_rows < CS_MAX_CHUNKS ? (total_rows > 0 ? total_rows : 1) : CS_MAX_CHUNKS);
@@ -408,10 +452,8 @@ cudaError_t launch_colsum(const ColsumArgs& a, cudaStream_t stream) {
   if (rows_per_chunk > 0) nchunks = static_cast<int>((total_rows + rows_per_chunk - 1) / rows_per_chunk);
   if (nchunks < 1) nchunks = 1;
   dim3 grid(nchunks, (a.cols / 8 + CS_THREADS - 1) / CS_THREADS);
-  colsum_partial_kernel<<<grid, CS_THREADS, 0, stream>>>(a, rows_per_chunk > 0 ? rows_per_chunk : 1);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  colsum_final_kernel<<<(a.cols + 31) / 32, CS_THREADS, 0, stream>>>(a, nchunks);
+  if (grid.y > CS_MAX_COLGROUPS) return cudaErrorInvalidValue;
+  colsum_kernel<<<grid, CS_THREADS, 0, stream>>>(a, rows_per_chunk > 0 ? rows_per_chunk : 1, nchunks);
   return cudaGetLastError();
 }
 

@@ -126,7 +126,7 @@ class ConnectorStep:
                            and (not self.use_a or free(s.audio_frames, p.audio_stride))
                            and (not self.use_v or free(s.video_frames, p.video_stride)))
         npack = int(self.use_a) + int(self.use_v)
-        self.launches_per_step = npack + (3 if self.direct else 5) + 2  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum x2
+        self.launches_per_step = npack + (3 if self.direct else 5) + 1  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
         # N > 1: optionally all-reduce the audio-weight span while the video-weight dW launch still runs.  Measured on
         # B200 x8 (profiles/README.md): NCCL needs ~48+ SMs to run at speed, which the persistent GEMM must give up, so
@@ -172,16 +172,20 @@ class ConnectorStep:
         e.record()
         self.events[name].append((s, e))
 
-    def _on_side(self, name, fn):
-        """Run a small HBM-bound kernel on the side stream, concurrently with the tensor-bound GEMM that follows on
-        the main stream (the GEMM's CTAs leave threads, registers and HBM bandwidth free on every SM).  Returns the
-        event the main stream must wait for before anything consumes the kernel's output."""
-        main = torch.cuda.current_stream()
+    def _fork(self):
+        """Point on the main stream after which side-stream work may start."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def _on_side(self, fork, name, fn):
+        """Run a small HBM-bound kernel on the side stream, concurrently with the tensor-bound GEMM that was just
+        enqueued on the main stream after `fork` (the GEMM's CTAs leave threads, registers and HBM bandwidth free on
+        every SM; enqueueing the GEMM FIRST lets its CTAs take their SMs before the small kernel's blocks fill them).
+        Returns the event the main stream must wait for before anything consumes the kernel's output."""
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=self.device)
         side = self._side_stream
-        fork = torch.cuda.Event()
-        fork.record(main)
         with torch.cuda.stream(side):
             side.wait_event(fork)
             self._timed(name, fn)
@@ -211,11 +215,11 @@ class ConnectorStep:
             xs = ([self.audio.view(self.M, self.Ka)] if self.use_a else []) + \
                  ([self.video.view(self.M, self.Kv)] if self.use_v else [])
             wsegs = ([self.wp[:, :self.Ka]] if self.use_a else []) + ([self.wp[:, self.Ka:]] if self.use_v else [])
-            if self.side_streams:
-                done = self._on_side("splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
+            fork = self._fork() if self.side_streams else None
             self._timed("proj_fwd", lambda: L.proj_fwd(xs, wsegs, self.emb_av, bias0=b0, bias1=b1, bias_scale0=s0,
                                                        bias_scale1=s1))
             if self.side_streams:
+                done = self._on_side(fork, "splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
                 torch.cuda.current_stream().wait_event(done)
             else:
                 self._timed("splice_fwd", lambda: L.splice_fwd(self.sp_text, None, self.emb))
@@ -250,22 +254,24 @@ class ConnectorStep:
         if allreduce and self.fused_allreduce:
             return self._backward_fused_allreduce(dy, base, xa, xv, dba, dbv, ga, gv, cs)
         overlap = allreduce and self.overlap_comm and g.world_size() > 1 and self.use_a and self.use_v
+        # the bias column sums only read d(inputs_embeds): run them under the dW GEMM
+        side_cs = self.side_streams and self.direct
+        fork = self._fork() if side_cs else None
         cs_done = None
-        if self.side_streams and self.direct:
-            # the bias column sums only read d(inputs_embeds): run them under the dW GEMM
-            cs_done = self._on_side("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv,
-                                                               **cs))
+
+        def bias_sums():
+            L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, **cs)
+
         if not overlap:
             xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
             dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
                   ([g["video_connector.linear.weight"]] if self.use_v else [])
             al = ([ga] if self.use_a else []) + ([gv] if self.use_v else [])
             self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, xs, dws, al, dy_row_base=base))
-            if cs_done is not None:
-                torch.cuda.current_stream().wait_event(cs_done)
+            if side_cs:
+                torch.cuda.current_stream().wait_event(self._on_side(fork, "colsum", bias_sums))
             else:
-                self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv,
-                                                       **cs))
+                self._timed("colsum", bias_sums)
             if allreduce:
                 g.allreduce(prescaled=pre)
             return g
@@ -278,6 +284,8 @@ class ConnectorStep:
         comm = self._comm_stream
         self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, [xa], [g["audio_connector.linear.weight"]], [ga],
                                                          dy_row_base=base))
+        if side_cs:
+            cs_done = self._on_side(fork, "colsum", bias_sums)
         e1 = torch.cuda.Event()
         e1.record(main)
         with torch.cuda.stream(comm):
@@ -289,7 +297,7 @@ class ConnectorStep:
         if cs_done is not None:
             main.wait_event(cs_done)
         else:
-            self._timed("colsum", lambda: L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, **cs))
+            self._timed("colsum", bias_sums)
         e2 = torch.cuda.Event()
         e2.record(main)
         with torch.cuda.stream(comm):
@@ -305,27 +313,29 @@ class ConnectorStep:
         the GEMM) and flag their ranges ready; the GEMM's comm warps reduce them together with the weight tiles."""
         g = self.bucket
         comm = g.peer.next_epoch()
-        H = self.shape.hidden
-        n0, n1 = (H if dba is not None else 0), (H if dbv is not None else 0)
         ex = [t for t in (dba, dbv) if t is not None]
 
-        def bias_sums():
-            L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, **cs)
-            L.comm_signal_extra(comm, ex[0].numel(), ex[1].numel() if len(ex) > 1 else 0)
+        def bias_sums():  # one launch; its last CTA flags the sums ready for this epoch
+            L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, comm=comm, **cs)
 
-        cs_done = None
-        if self.side_streams:
-            cs_done = self._on_side("colsum", bias_sums)
-        else:
-            self._timed("colsum", bias_sums)
         xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
         dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
               ([g["video_connector.linear.weight"]] if self.use_v else [])
         al = ([ga] if self.use_a else []) + ([gv] if self.use_v else [])
-        self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw_allreduce(
-            dy, xs, dws, al, comm, extra0=ex[0], extra1=ex[1] if len(ex) > 1 else None, dy_row_base=base))
-        if cs_done is not None:
-            torch.cuda.current_stream().wait_event(cs_done)
+
+        def gemm():
+            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw_allreduce(
+                dy, xs, dws, al, comm, extra0=ex[0], extra1=ex[1] if len(ex) > 1 else None, dy_row_base=base))
+
+        if self.side_streams:
+            # GEMM first (its CTAs take the SMs), bias sums next to it: they use no shared memory and few registers,
+            # so their blocks fit beside the GEMM CTAs and finish long before the GEMM's comm warps need them
+            fork = self._fork()
+            gemm()
+            torch.cuda.current_stream().wait_event(self._on_side(fork, "colsum", bias_sums))
+        else:
+            self._timed("colsum", bias_sums)
+            gemm()
         return g
 
     def step(self, allreduce: bool = True):

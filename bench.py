@@ -295,6 +295,16 @@ def main():
                "sample": f"batch {sb} of {w['batch_per_gpu']} (same shapes), {sw} warm-up + {ss} timed fwd+bwd steps, "
                          f"fp32 torch CPU oracle port ({dt:.2f} s/step)"}
 
+    if world == 1:
+        collective = "none"
+    elif eng.fused_allreduce:
+        collective = ("projector-grad all-reduce fused into the dW GEMM launch (100.7 MB fp32 flat bucket in peer-mapped "
+                      "memory: comm warps of the GEMM CTAs sum finished tiles over NVLink with peer loads / stores "
+                      "while later tiles are computed)")
+    else:
+        collective = ("projector-grad all-reduce (NCCL sum of pre-scaled grads, 100.7 MB fp32 flat bucket; " +
+                      ("audio-weight span overlapped with the video-weight dW launch)" if eng.overlap_comm
+                       else "one call after the backward)"))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,12 +314,7 @@ def main():
                    "parallelism": f"dp{world}", "step": ("fused: tower outputs -> 2-segment GEMM whose epilogue writes the AV rows of inputs_embeds -> text rows + masks; "
                                                         "dW GEMM and bias sums read d(inputs_embeds) in place"
                                                        if eng.direct else "gather -> GEMM -> splice; splice-bwd -> dW GEMM"),
-                   "collective": (("projector-grad all-reduce fused into the dW GEMM launch (100.7 MB fp32 flat bucket in "
-                                   "peer-mapped memory: comm warps of the GEMM CTAs sum finished tiles over NVLink "
-                                   "with peer loads / stores while later tiles are computed)") if eng.fused_allreduce
-                                  else ("projector-grad all-reduce (NCCL sum of pre-scaled grads, 100.7 MB fp32 flat bucket" +
-                                        ("; audio-weight span overlapped with the video-weight dW launch)" if eng.overlap_comm
-                                         else "; one call after the backward)"))) if world > 1 else "none"),
+                   "collective": collective,
                    "l2": "no flush: one step streams ~0.9 GB (features, A, W, Y, embeds, grads) >> 126 MB L2"},
         "roofline": roofline, "kernels": kernels, "unfused_step": unfused, "cpu_baseline": cpu, "e2e": e2e,
         "clocks": clocks,

@@ -144,13 +144,23 @@ AVC_API int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, in
 /* Enqueue after the kernel that wrote this rank's extra ranges (same stream): flags them ready for comm->epoch. */
 AVC_API int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extra1_len, void* stream);
 
-/* ---- bias gradient: deterministic two-pass column sum over flagged rows -------------------------
+/* ---- bias gradient: deterministic column sum over flagged rows (one launch, fixed summation tree) -------------
  * out_i[c] = alpha_i * sum_{b, r < sum_rows : flag_i(b, r)} dY[b, dy_row_base + r, c]      (db = sum dY)
- * flags: row_flags[b * sum_rows + r] bit i, or (r < flag_rows_i) when row_flags is NULL. */
+ * flags: row_flags[b * sum_rows + r] bit i, or (r < flag_rows_i) when row_flags is NULL.
+ * workspace: avc_colsum_workspace_bytes(cols) bytes, 16-byte aligned; its first avc_colsum_workspace_header_bytes()
+ * bytes (arrival counters) must be ZERO before the first call -- every call leaves them zero again.  Calls that share
+ * a workspace must be ordered on one stream.  The kernel uses no shared memory, so it can run next to the projector
+ * GEMM on another stream.
+ * avc_colsum_comm: the same, and when the sums are final it flags them ready for comm->epoch's fused all-reduce
+ * (what avc_comm_signal_extra would do after it), out0 / out1 being the extra ranges of that launch. */
 AVC_API size_t avc_colsum_workspace_bytes(int32_t cols);
+AVC_API size_t avc_colsum_workspace_header_bytes(void);
 AVC_API int avc_colsum(const avc_mat* dy /* bf16 */, int32_t dy_row_base, int32_t sum_rows,
                const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, float alpha0,
                float alpha1, float* out0, float* out1, void* workspace, void* stream);
+AVC_API int avc_colsum_comm(const avc_mat* dy /* bf16 */, int32_t dy_row_base, int32_t sum_rows,
+               const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, float alpha0,
+               float alpha1, float* out0, float* out1, void* workspace, const avc_comm* comm, void* stream);
 
 /* ---- weight pack: W_bf16 = bf16(alpha * W_fp32) (folds fusion_scale into the projector) -------- */
 AVC_API int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows,
