@@ -398,7 +398,10 @@ int avc_comm_alloc(size_t bytes, void** ptr) {
   if (int rc = device_info(&di)) return rc;
   if (ptr == nullptr || bytes == 0) return fail(AVC_ERR_INVALID, "comm_alloc: bad argument");
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
+  cudaError_t e = avc::preload_comm_kernels();
+  if (e == cudaSuccess) e = avc::preload_colsum();
+  if (e != cudaSuccess) return cuda_fail(e, "comm_alloc kernel preload");
+  e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) return cuda_fail(e, "comm_alloc cudaMalloc");
   e = cudaMemset(p, 0, bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();

@@ -44,6 +44,7 @@ struct CommArgs {
   int extra_len[2];                 //   (the bias gradients; multiples of 4 floats, 16-byte aligned)
   int32_t* status;                  // local device word: COMM_ERR_* on failure
   uint64_t timeout_ns;              // give up (status = timeout) instead of hanging when a peer never shows up
+  uint32_t poll_ns;                 // set by launch_gemm: sleep between two polls of a flag
 };
 
 struct GemmArgs {
@@ -99,6 +100,10 @@ cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int 
 int gemm_work_items(const GemmArgs& args, int cta_group, int num_sms);
 // flags every owner that this rank's extra ranges (bias gradients) hold their partial sums for `epoch`
 cudaError_t launch_comm_signal_extra(const CommArgs& comm, cudaStream_t stream);
+// Force-load the kernels that get launched while a fused GEMM is already waiting for them (lazy module loading can
+// block behind running kernels): colsum and the signal kernel.
+cudaError_t preload_comm_kernels();
+cudaError_t preload_colsum();
 
 // ------------------------------------------------------------------ gather (align + stack + concat)
 struct GatherArgs {

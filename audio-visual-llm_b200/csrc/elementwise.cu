@@ -438,6 +438,13 @@ size_t colsum_workspace_bytes(int cols) {
 }
 size_t colsum_workspace_header_bytes() { return static_cast<size_t>(CS_HEADER_WORDS) * sizeof(float); }
 
+// CUDA loads kernels lazily, and loading one can wait for running kernels to finish.  colsum_kernel is launched
+// while the fused dW + all-reduce GEMM is already spinning on its result, so it must be resident before that.
+cudaError_t preload_colsum() {
+  cudaFuncAttributes attr;
+  return cudaFuncGetAttributes(&attr, colsum_kernel);
+}
+
 cudaError_t launch_colsum(const ColsumArgs& a, cudaStream_t stream) {
   if (a.cols <= 0) return cudaSuccess;
   if (a.cols % 8 != 0 || a.row_stride % 16 != 0 || a.batch_stride % 16 != 0 ||

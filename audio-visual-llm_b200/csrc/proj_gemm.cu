@@ -72,9 +72,13 @@ __device__ __forceinline__ bool comm_wait(const uint32_t* f, const CommArgs& cm,
   uint64_t t0 = 0;
   uint32_t spins = 0;
   for (;;) {
-    const uint32_t v = lane < cm.world ? ld_acquire_sys(f + lane) : cm.epoch;
-    if (__all_sync(0xffffffffu, static_cast<int32_t>(v - cm.epoch) >= 0)) return true;
-    __nanosleep(128);
+    // relaxed polls (no cache maintenance per poll), one acquire fence once every flag has arrived
+    const uint32_t v = lane < cm.world ? ld_relaxed_sys_u32(f + lane) : cm.epoch;
+    if (__all_sync(0xffffffffu, static_cast<int32_t>(v - cm.epoch) >= 0)) {
+      fence_acq_rel_sys();
+      return true;
+    }
+    __nanosleep(cm.poll_ns);
     if ((++spins & 0x7fu) == 0) {
       int bail = 0;
       if (lane == 0) {
@@ -619,6 +623,7 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
   const int workers = plan_schedule<CG>(args, mode, num_sms);
   const bool comm = args.comm.world > 0;
   if (comm && !(mode == GEMM_NT && out_fp32 && CG == 2)) return cudaErrorInvalidValue;
+  args.comm.poll_ns = static_cast<uint32_t>(env_int("AVC_COMM_POLL_NS", 200));
   auto run = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG, MT>::SMEM_ALLOC);
     if (e != cudaSuccess) return e;
@@ -703,6 +708,11 @@ int gemm_work_items(const GemmArgs& args_in, int cta_group, int num_sms) {
   else plan_schedule<1>(args, GEMM_NT, num_sms);
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
   return args.full_tiles + (num_tiles - args.full_tiles) * args.tail_split;
+}
+
+cudaError_t preload_comm_kernels() {
+  cudaFuncAttributes attr;
+  return cudaFuncGetAttributes(&attr, comm_signal_extra_kernel);
 }
 
 cudaError_t launch_comm_signal_extra(const CommArgs& comm, cudaStream_t stream) {

@@ -54,6 +54,13 @@ class PeerMemory:
                 self.flag_ptrs.append(pf)
         self.flat = L.as_tensor(self._own[0], nfloats, torch.float32, self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # The bias-sum kernel is launched while the fused GEMM already waits for it; CUDA loads kernels lazily and a
+        # load can block behind running kernels, so run it once now (avc_comm_alloc also preloads it).
+        with torch.cuda.device(self.device):
+            warm = torch.zeros(1, 8, 64, dtype=torch.bfloat16, device=self.device)
+            out = torch.empty(64, dtype=torch.float32, device=self.device)
+            L.colsum(warm, out, None, L.colsum_workspace(64, self.device))
+            torch.cuda.synchronize(self.device)
         self.timeout_ns = int(timeout_s * 1e9)
         self.epoch = 0
         if self.world > 1:
