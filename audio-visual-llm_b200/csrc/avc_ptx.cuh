@@ -221,16 +221,19 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
+// Bulk data of the all-reduce: plain (weak) 16-byte accesses, ordered by the system-scope acquire that precedes the
+// loads (flag wait + fence.acq_rel.sys, which also drops stale L1 lines of peer memory) and by the fence + release
+// store that follows the stores.  L1::no_allocate: every line is touched once.
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {
   float4 r;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p)
                : "memory");
   return r;
 }
-__device__ __forceinline__ void st_relaxed_sys_v4(float* p, const float4& v) {
-  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+__device__ __forceinline__ void st_peer_v4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
                : "memory");
 }

@@ -114,7 +114,7 @@ __device__ __forceinline__ void comm_reduce_rows(const CommArgs& cm, int64_t bas
         off[c] = base + static_cast<int64_t>(r) * ld + 4 * (v - r * nvec);
 #pragma unroll
         for (int p = 0; p < W; ++p)
-          if (p < world) x[c][p] = ld_relaxed_sys_v4(cm.data[p] + off[c]);
+          if (p < world) x[c][p] = ld_peer_v4(cm.data[p] + off[c]);
       }
     }
 #pragma unroll
@@ -126,7 +126,7 @@ __device__ __forceinline__ void comm_reduce_rows(const CommArgs& cm, int64_t bas
         if (p < world) { s.x += x[c][p].x; s.y += x[c][p].y; s.z += x[c][p].z; s.w += x[c][p].w; }
 #pragma unroll
       for (int p = 0; p < W; ++p)
-        if (p < world) st_relaxed_sys_v4(cm.data[p] + off[c], s);
+        if (p < world) st_peer_v4(cm.data[p] + off[c], s);
     }
   }
 }

@@ -13,6 +13,7 @@ single NCCL call.
 from __future__ import annotations
 
 import os
+import sys
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -82,8 +83,18 @@ class ConnectorStep:
         if fused_allreduce is None:
             fused_allreduce = ddp and dist.get_world_size(process_group) > 1 and \
                 os.environ.get("AVC_FUSED_ALLREDUCE", "1") != "0"
+        if fused_allreduce and ddp and dist.get_world_size(process_group) > L.COMM_MAX_WORLD:
+            fused_allreduce = False  # the flag layout holds COMM_MAX_WORLD ranks; larger jobs all-reduce through NCCL
         self.fused_allreduce = bool(fused_allreduce)
-        self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce)
+        try:
+            self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce)
+        except L.ConnectorError as e:
+            if not (self.fused_allreduce and ddp):
+                raise
+            # no peer mapping between the GPUs (PeerMemory agreed on the failure across ranks): NCCL all-reduce
+            print(f"[avc] fused gradient all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            self.fused_allreduce = False
+            self.bucket = GradBucket(sizes, dev, process_group=process_group)
         # ---- inputs resident in HBM
         self.audio = randn(s.batch, s.audio_frames, s.audio_dim).to(bf).to(dev) if self.use_a else None
         self.video = randn(s.batch, s.video_frames, s.video_dim).to(bf).to(dev) if self.use_v else None

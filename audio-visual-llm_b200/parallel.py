@@ -44,14 +44,33 @@ class PeerMemory:
                 handles = [None] * self.world
                 dist.all_gather_object(handles, mine, group=process_group)
             self.bucket_ptrs, self.flag_ptrs, self._opened = [], [], []
-            for r, (hb, hf) in enumerate(handles):
-                if r == self.rank:
-                    pb, pf = self._own
-                else:
-                    pb, pf = L.comm_open(hb), L.comm_open(hf)
-                    self._opened += [pb, pf]
-                self.bucket_ptrs.append(pb)
-                self.flag_ptrs.append(pf)
+            err = None
+            try:
+                for r, (hb, hf) in enumerate(handles):
+                    if r == self.rank:
+                        pb, pf = self._own
+                    else:
+                        pb = L.comm_open(hb)
+                        self._opened.append(pb)
+                        pf = L.comm_open(hf)
+                        self._opened.append(pf)
+                    self.bucket_ptrs.append(pb)
+                    self.flag_ptrs.append(pf)
+            except L.ConnectorError as e:  # e.g. no peer access between two GPUs
+                err = e
+            if self.world > 1:
+                # every rank must reach the same verdict, or some would wait for flags that never come
+                ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+                if int(ok.item()) == 0 and err is None:
+                    err = L.ConnectorError("another rank could not map the peer buffers")
+            if err is not None:
+                for p in self._opened:
+                    L.comm_close(p)
+                for p in self._own:
+                    L.comm_free(p)
+                self._opened, self._own = [], None
+                raise L.ConnectorError(f"peer-memory setup failed on rank {self.rank}: {err}")
         self.flat = L.as_tensor(self._own[0], nfloats, torch.float32, self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         # The bias-sum kernel is launched while the fused GEMM already waits for it; CUDA loads kernels lazily and a
