@@ -199,7 +199,15 @@ def main():
     if "proj_bwd_dw_v" in kernel_ms:  # N > 1: the dW GEMM runs as two launches (all-reduce overlap)
         kernel_ms["proj_bwd_dw"] += kernel_ms.pop("proj_bwd_dw_v")
     eng.events = None
+    per_rank = None
     if world > 1:
+        # every rank's GEMM times: ranks run at different power-capped clocks, and the fused dW + all-reduce launch
+        # (like any all-reduce) ends with the slowest rank
+        mine = torch.tensor([kernel_ms.get("proj_fwd", 0.0), kernel_ms.get("proj_bwd_dw", 0.0)], device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"proj_fwd_ms": [round(float(x[0]), 4) for x in allr],
+                    "proj_bwd_dw_ms": [round(float(x[1]), 4) for x in allr]}
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
@@ -316,7 +324,7 @@ def main():
                                                        if eng.direct else "gather -> GEMM -> splice; splice-bwd -> dW GEMM"),
                    "collective": collective,
                    "l2": "no flush: one step streams ~0.9 GB (features, A, W, Y, embeds, grads) >> 126 MB L2"},
-        "roofline": roofline, "kernels": kernels, "unfused_step": unfused, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "kernels": kernels, "per_rank_kernel_ms": per_rank, "unfused_step": unfused, "cpu_baseline": cpu, "e2e": e2e,
         "clocks": clocks,
         "gpu_launches": eng.launches_per_step * args.steps,
     }
