@@ -72,13 +72,16 @@ __device__ __forceinline__ bool comm_wait(const uint32_t* f, const CommArgs& cm,
   uint64_t t0 = 0;
   uint32_t spins = 0;
   for (;;) {
-    // relaxed polls (no cache maintenance per poll), one acquire fence once every flag has arrived
+    // Relaxed polls; once every flag has arrived, an ACQUIRE load of the same words orders the data loads behind the
+    // flags.  Not a fence: fence.acq_rel.sys (MEMBAR.SYS) also waits until this warp's earlier peer stores are
+    // acknowledged system-wide, which measured ~4 us per wait (ncu: stall_membar dominated the comm warps).
     const uint32_t v = lane < cm.world ? ld_relaxed_sys_u32(f + lane) : cm.epoch;
     if (__all_sync(0xffffffffu, static_cast<int32_t>(v - cm.epoch) >= 0)) {
-      fence_acq_rel_sys();
+      if (lane < cm.world) (void)ld_acquire_sys(f + lane);
+      __syncwarp();
       return true;
     }
-    __nanosleep(cm.poll_ns);
+    if (cm.poll_ns != 0) __nanosleep(cm.poll_ns);  // measured: 0 .. 20 us makes no difference to the launch time
     if ((++spins & 0x7fu) == 0) {
       int bail = 0;
       if (lane == 0) {
@@ -489,12 +492,12 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           const CommArgs& cm = args.comm;
           bulk_wait_all<0>();
           fence_proxy_async_all();
-          __threadfence_system();
+          __threadfence();  // gpu scope is enough up to the arrival counter; the last arriver fences at system scope
           uint32_t* lf = cm.flags[cm.rank];
           if (atomicAdd(lf + COMM_ITEM_COUNT + w, 1u) == EPI_WARPS * CG - 1) {
             atomicExch(lf + COMM_ITEM_COUNT + w, 0u);
-            __threadfence_system();
-            st_release_sys(cm.flags[w % cm.world] + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD + cm.rank, cm.epoch);
+            __threadfence_system();  // acquires the other warps' arrivals, releases the flag store below
+            st_relaxed_sys_u32(cm.flags[w % cm.world] + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD + cm.rank, cm.epoch);
           }
         }
         __syncwarp();
@@ -509,28 +512,37 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     const int G = static_cast<int>(gridDim.x) * COMM_WARPS;
     uint32_t* lf = cm.flags[cm.rank];
     constexpr int RG = TILE_M / COMM_UNIT_ROWS;  // row groups (units) per work item
-    const int n_owned = total_work > cm.rank ? (total_work - cm.rank + cm.world - 1) / cm.world : 0;
     bool ok = true;
     int cur = -1;
-    // units of the items this rank owns, in schedule order (= completion order), dealt round-robin to the comm warps
-    for (int u = g; ok && u < n_owned * RG; u += G) {
-      const int i = u / RG;
-      const int w = cm.rank + i * cm.world;
-      if (w != cur) {
-        ok = comm_wait(lf + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD, cm, lane);
-        cur = w;
-        if (!ok) break;
+    // The schedule's rounds (num_workers items each) complete one after the other, the items of one round together.
+    // Per round, the units of the items this rank owns are dealt to the GPU's comm warps in CONTIGUOUS runs, so a warp
+    // waits for (and pays the system-scope acquire of) one or two items per round instead of one per unit.
+    for (int r0 = 0; ok && r0 < total_work; r0 += num_workers) {
+      const int r1 = r0 + num_workers < total_work ? r0 + num_workers : total_work;
+      const int first = r0 + (cm.rank - r0 % cm.world + cm.world) % cm.world;  // first owned item of the round
+      const int n_own = first < r1 ? (r1 - first + cm.world - 1) / cm.world : 0;
+      const int units = n_own * RG;
+      const int per = (units + G - 1) / G;
+      const int l1 = (g + 1) * per < units ? (g + 1) * per : units;
+      for (int l = g * per; l < l1; ++l) {
+        const int i = l / RG;
+        const int w = first + i * cm.world;
+        if (w != cur) {
+          ok = comm_wait(lf + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD, cm, lane);
+          cur = w;
+          if (!ok) break;
+        }
+        int m_blk, n_blk, n_off, width;
+        decode(w, m_blk, n_blk, n_off, width);
+        const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
+        const int ld = args.d_cols[seg];
+        const int col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off;
+        const int row0 = m_blk * TILE_M + (l - i * RG) * COMM_UNIT_ROWS;
+        const int rows = min(COMM_UNIT_ROWS, args.d_rows - row0);
+        const int cols = min(width, ld - col0);
+        if (rows <= 0 || cols <= 0) continue;
+        comm_reduce<COMM>(cm, cm.seg_off[seg] + static_cast<int64_t>(row0) * ld + col0, ld, rows, cols >> 2, lane);
       }
-      int m_blk, n_blk, n_off, width;
-      decode(w, m_blk, n_blk, n_off, width);
-      const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
-      const int ld = args.d_cols[seg];
-      const int col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off;
-      const int row0 = m_blk * TILE_M + (u - i * RG) * COMM_UNIT_ROWS;
-      const int rows = min(COMM_UNIT_ROWS, args.d_rows - row0);
-      const int cols = min(width, ld - col0);
-      if (rows <= 0 || cols <= 0) continue;
-      comm_reduce<COMM>(cm, cm.seg_off[seg] + static_cast<int64_t>(row0) * ld + col0, ld, rows, cols >> 2, lane);
     }
     // extra flat ranges (bias gradients, produced by another kernel): 128-float chunks, chunk e owned by rank
     // e % world, the owner's chunks dealt to its comm warps from the back of the warp list
@@ -558,7 +570,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       if (atomicAdd(lf + COMM_DONE_COUNT, 1u) == static_cast<uint32_t>(G - 1)) {
         atomicExch(lf + COMM_DONE_COUNT, 0u);
         __threadfence_system();
-        for (int p = 0; p < cm.world; ++p) st_release_sys(cm.flags[p] + COMM_DONE_FLAGS + cm.rank, cm.epoch);
+        for (int p = 0; p < cm.world; ++p) st_relaxed_sys_u32(cm.flags[p] + COMM_DONE_FLAGS + cm.rank, cm.epoch);
         last = 1;
       }
     }

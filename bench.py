@@ -47,12 +47,14 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms.  Started BEFORE the warm-up (nvidia-smi takes a few
+    hundred ms to produce its first line) and windowed to the timed region by wall-clock time stamps."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -68,7 +70,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) >= 6:
-                self.rows.append(parts)
+                self.rows.append((time.time(), parts))
+
+    def wait_first_sample(self, timeout_s: float = 5.0):
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout_s:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -78,9 +91,20 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        rows = self.rows
+        if self.t0 is not None and self.t1 is not None:
+            inside = [r for r in rows if self.t0 <= r[0] <= self.t1 + 0.03]
+            window = "timed region"
+            if not inside and rows:  # region shorter than the sampling period: take the samples closest to it
+                mid = 0.5 * (self.t0 + self.t1)
+                inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+                window = "nearest samples to the timed region"
+            rows = inside
+        else:
+            window = "whole run"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for _, r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -91,7 +115,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def reference_arm(args, rank: int):
@@ -118,7 +142,7 @@ def reference_arm(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -177,23 +201,27 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ device-resident throughput (`value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         eng.step()
     barrier()
     eng.enable_kernel_timing()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first_sample()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     t_start.record()
     for _ in range(args.steps):
         eng.step()
     t_end.record()
     barrier()
+    sampler.mark_end()
     elapsed_ms = t_start.elapsed_time(t_end)
     if rank == 0:
-        time.sleep(0.15)
+        time.sleep(0.05)
     clocks = sampler.stop() if rank == 0 else None
     kernel_ms = {n: sum(s.elapsed_time(e) for s, e in ev) / len(ev) for n, ev in eng.events.items() if ev}
     if "proj_bwd_dw_v" in kernel_ms:  # N > 1: the dW GEMM runs as two launches (all-reduce overlap)
