@@ -15,10 +15,27 @@ for name, v in d["kernels"].items():
         rows.append(f"| {name} | {v['ms'] * 1e3:.1f} | {v['GBps']:.0f} GB/s | {v['frac_hbm'] * 100:.1f} % of measured HBM copy "
                     f"(6555 GB/s) |")
 scal = []
-for n, f in ((1, "r01_bench_n1.json"), (4, "r01_bench_n4_overlap16.json"), (8, "r01_bench_n8_overlap16.json")):
+base = None
+for n in (1, 2, 4, 8):
+    f = f"r01_bench_n{n}.json"
     if (P / f).exists():
         x = json.loads((P / f).read_text())
-        scal.append(f"| {x['n_gpus']} | {x['ms_per_step']:.4f} | {x['value'] / 1e6:.2f} M | {x['e2e']['value'] / 1e6:.2f} M | {f} |")
+        if n == 1:
+            base = x["value"]
+        e2 = x.get("e2e")
+        pr = x.get("per_rank_kernel_ms") or {}
+        dw = pr.get("proj_bwd_dw_ms")
+        scal.append(f"| {x['n_gpus']} | {x['ms_per_step']:.4f} | {x['value'] / 1e6:.2f} M | "
+                    f"{x['value'] / (base * n) * 100 if base else 0:.0f} % | "
+                    f"{('%.2f M' % (e2['value'] / 1e6)) if e2 else 'not run'} | "
+                    f"{x['kernels']['proj_fwd']['ms']:.3f} / {x['kernels']['proj_bwd_dw']['ms']:.3f}"
+                    f"{' (ranks: %.3f-%.3f)' % (min(dw), max(dw)) if dw else ''} | {f} |")
+nccl = []
+for n in (2, 8):
+    f = f"r01_bench_n{n}_nccl_allreduce.json"
+    if (P / f).exists():
+        x = json.loads((P / f).read_text())
+        nccl.append(f"| {n} | {x['ms_per_step']:.4f} | {x['value'] / 1e6:.2f} M | {x['kernels']['proj_bwd_dw']['ms']:.3f} | {f} |")
 e = d["e2e"]
 text = f"""# profiles/ — round 1 evidence (B200, sm_100a)
 
@@ -36,7 +53,7 @@ tests, NaN-poisoned outputs and bounds-clipped TMA boxes.
 | `cpu_baseline` (oracle port, {d['cpu_baseline']['cores']} host threads) | {d['cpu_baseline']['value'] / 1e3:.1f} k fused tokens/s |
 | `roofline` (projector GEMM, fwd + dW launches averaged) | {d['roofline']['achieved']:.0f} TFLOP/s = {d['roofline']['frac'] * 100:.1f} % of the {'sustained' if d['roofline']['peak'] < 1500 else 'burst'} cuBLAS peak ({d['roofline']['frac_of_burst_peak'] * 100:.1f} % of burst) |
 | clocks during the timed region | median {d['clocks']['sm_mhz']} MHz of {d['clocks']['sm_max_mhz']} MHz, reasons {d['clocks']['reasons']} (no thermal / hw slowdown) |
-| unfused step (stand-alone gather + splice kernels) | {d['unfused_step']['ms_per_step']:.4f} ms / step, 9 launches |
+| unfused step (stand-alone gather + splice kernels) | {d['unfused_step']['ms_per_step']:.4f} ms / step, {d['unfused_step']['launches_per_step']} launches |
 
 Per kernel (CUDA events inside the timed region; "stand-alone" rows come from the unfused step; in the fused step the
 text-row splice and the bias sums run on a side stream UNDER the GEMMs, so their wall time is not additive):
@@ -45,22 +62,38 @@ text-row splice and the bias sums run on a side stream UNDER the GEMMs, so their
 |---|---|---|---|
 """ + "\n".join(rows) + """
 
-Weak scaling (32 samples / GPU; `value` / `e2e` are whole-job):
+Weak scaling (32 samples / GPU; whole-job numbers; every N on its own `gpurun` box, so the "vs N x (N = 1)" column mixes
+box-to-box variation of about +-5 % into the efficiency; the driver's scaling run uses one box).  At N > 1 the gradient
+all-reduce runs INSIDE the dW GEMM launch over peer-mapped memory (DESIGN.md section 6), so the dW column contains it:
 
-| N | ms / step | value (fused tok/s) | e2e (fused tok/s) | file |
-|---|---|---|---|---|
+| N | ms / step | value (fused tok/s) | vs N x (N = 1) | e2e (fused tok/s) | fwd / dW(+all-reduce) launch ms | file |
+|---|---|---|---|---|---|---|
 """ + "\n".join(scal) + """
 
-(The N = 4 / 8 files were taken with the overlapped all-reduce schedule and the round's earlier GEMM; with the plain
-all-reduce now default N = 8 measured 1.3154 ms / step = 73.0 M tok/s. e2e at N > 1 is bound by host-memory / PCIe
-bandwidth shared by the GPUs: 23.6 GB/s per GPU at N = 8 against 54.6 GB/s alone.)
+The same step with one NCCL all-reduce after the backward (`AVC_FUSED_ALLREDUCE=0`, the round's previous default):
+
+| N | ms / step | value (fused tok/s) | plain dW launch ms | file |
+|---|---|---|---|---|
+""" + "\n".join(nccl) + """
+
+`r01_dp_check_n8.log`, `r01_dp_check_n2_cfg2.log`: `tools/dp_check.py` under torchrun -- the fused, NCCL and overlapped
+schedules give the same reduced gradients (<= 1.3e-7 of an fp64 mean) and every rank ends with bit-identical buckets.
+e2e at N > 1 moves 147.6 MB per GPU per step from pinned host memory and is PCIe-bound per GPU.
 
 ## ncu
 
 * `r01_launches_bench_steps3.csv` — `ncu --metrics gpu__time_duration.sum` launch list of
   `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e` (cold-cache, serialised). Shares of the step agree
   with the CUDA-event breakdown above: the two `gemm_kernel` launches are ~ 88 % of the step.
-* `r01_kernels_full.md/.json` — `ncu --set full` summary of the fused step's kernels (GEMM TN / NT, splice, colsum);
+* `r01_fused_dw_kernels_full.md/.json` — `ncu --set full` of `tools/fused_ar_probe.py --ncu` (one GPU): the one-launch
+  `colsum_kernel` (46 us, 98.3 MB read = the algorithmic bytes), the plain dW GEMM `gemm_kernel<1,1,2,2,0>` (416 us) and
+  the dW GEMM with the all-reduce protocol fused in at world = 1, `gemm_kernel<1,1,2,2,1>` (457 us: every tile is
+  re-read and re-written by the comm warps; tensor pipe 70 % vs 79 % of elapsed cycles).  The first version of the
+  fused kernel took 506 us; the source page showed the comm warps stalled on `ERRBAR` / `stall_membar` (system-scope
+  fences after every flag wait, ~4 us each) -> acquire LOADS instead of fences on the wait path, one or two waits per
+  schedule round instead of one per 8-row unit, gpu-scope fence in the epilogue: 457 us.
+* `r01_kernels_full.md/.json` — `ncu --set full` summary of the fused step's kernels (GEMM TN / NT, splice; its
+  `colsum_partial/final` kernels are the round's earlier two-launch version);
   `r01_standalone_kernels_full.md/.json` — the same for the stand-alone kernels incl. gather (147.5 MB read,
   147.5 MB written = exactly the algorithmic bytes; 66 % of ncu's DRAM peak) and splice fwd / bwd.
   GEMM: tensor pipe active 80 % (fwd) / 69-71 % (dW, 256-row tiles) of elapsed cycles, DRAM at 17-27 % of peak, L2 / XBAR
@@ -86,8 +119,20 @@ bandwidth shared by the GPUs: 23.6 GB/s per GPU at N = 8 against 54.6 GB/s alone
    kernels on a side stream under the GEMMs (-2 %).
 4. TMA stores may overrun a tensor dimension (clipped) but fault on negative start coordinates -> the scatter
    epilogue stores sample-straddling boxes row by row.
-5. N > 1: the all-reduce of the 100.7 MB bucket alone takes 0.23 ms (N = 2) / 0.32 ms (N = 8); overlapping it with
-   the second dW launch needs ~48+ free SMs for NCCL and is no faster than one call after the backward.
+5. N > 1: the NCCL all-reduce of the 100.7 MB bucket alone takes 0.23 ms (N = 2) / 0.32 ms (N = 8); overlapping it
+   with the second dW launch needs ~48+ free SMs for NCCL and is no faster than one call after the backward.  Moving
+   the all-reduce INTO the dW GEMM (comm warps + peer loads / stores, no SMs given up) is: 1.05 vs 1.17 ms / step at
+   N = 2, 1.13 vs 1.31 ms at N = 8 (+16 % throughput).  At N = 8 the fused launch (0.65 ms against 0.43 ms for the plain
+   dW) is bound by the peer traffic of the pull-then-push scheme (176 MB per direction per GPU, ~350 GB/s effective);
+   next: push-only transport (TMA stores of partial tiles straight into the owner's staging area) or NVLS
+   `multimem.ld_reduce` / `multimem.st`, which moves 100 MB per direction.
+6. CUDA loads kernels lazily, and loading one can wait for running kernels: the first fused launch spun for its whole
+   20 s timeout waiting for a bias-sum kernel that could not be loaded while it ran -> the kernels launched next to a
+   waiting GEMM are preloaded (`avc_comm_alloc`).
+7. A kernel that must run next to a GEMM CTA owning all 228 KB of shared memory needs ZERO static shared memory (the
+   old two-launch column sum's final kernel used 2 KB and waited for GEMM CTAs to exit: 0.32 ms "under" the GEMM);
+   the one-launch version reduces across CTAs with last-arriver counters and `__syncthreads_or`: 0.12 ms next to the
+   GEMM, 46 us alone.
 """
 (P / "README.md").write_text(text)
 print(text[:1800])
