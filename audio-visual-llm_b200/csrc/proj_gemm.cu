@@ -6,10 +6,12 @@
 // This replaces the two nn.Linear calls + pad + weighted sum of the reference
 // (modality_connector.py:43-44, clip_whisper_model.py:424-434) and their autograd dW.
 //
-// Structure: persistent CTAs, 6 warps:
+// Structure: persistent CTAs, 6 warps (10 with the fused gradient all-reduce):
 //   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      tcgen05.mma issuer (one thread), owns the TMEM allocation (512 columns = 2 accumulators)
 //   warps 2..5  epilogue: tcgen05.ld (TMEM -> registers) -> bias/GELU/scale -> swizzled smem -> TMA store
+//   warps 6..9  (COMM != 0, data-parallel dW only) all-reduce of finished gradient tiles over peer-mapped memory:
+//               wait for every rank's "tile ready" flag, peer loads, sum in rank order, peer stores to every rank
 // The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // CG = 1: one CTA per SM computes a 128 x bn tile (4 stages of 16 KB A + 32 KB B).
