@@ -22,6 +22,8 @@ EXPORTS = (
     "avc_gelu_fwd", "avc_gelu_bwd", "avc_pack_weight_t",
     "avc_comm_flag_bytes", "avc_comm_alloc", "avc_comm_free", "avc_comm_export", "avc_comm_open", "avc_comm_close",
     "avc_proj_bwd_dw_allreduce", "avc_comm_signal_extra", "avc_colsum_comm", "avc_colsum_workspace_header_bytes",
+    "avc_mc_supported", "avc_mc_padded_bytes", "avc_mc_create", "avc_mc_import", "avc_mc_add_device",
+    "avc_mc_bucket_alloc", "avc_mc_bucket_free",
 )
 
 
@@ -58,8 +60,13 @@ class AvcComm(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
         ("bucket", C.c_void_p * COMM_MAX_WORLD), ("flags", C.c_void_p * COMM_MAX_WORLD), ("status", C.c_void_p),
-        ("timeout_ns", C.c_uint64), ("bucket_bytes", C.c_uint64),
+        ("timeout_ns", C.c_uint64), ("bucket_bytes", C.c_uint64), ("mc_bucket", C.c_void_p),
     ]
+
+
+class AvcMcBucket(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("mc_ptr", C.c_void_p), ("bytes", C.c_uint64), ("mem_handle", C.c_uint64),
+                ("mc_handle", C.c_uint64)]
 
 
 class ConnectorError(RuntimeError):
@@ -210,6 +217,46 @@ def comm_open(handle: bytes) -> int:
 
 def comm_close(ptr: int) -> None:
     check(load().avc_comm_close(C.c_void_p(ptr)))
+
+
+# NVSwitch multicast bucket (optional transport of the fused all-reduce)
+def mc_supported(device: int) -> bool:
+    v = C.c_int32(0)
+    check(load().avc_mc_supported(C.c_int32(device), C.byref(v)))
+    return bool(v.value)
+
+
+def mc_padded_bytes(world: int, min_bytes: int) -> int:
+    v = C.c_uint64(0)
+    check(load().avc_mc_padded_bytes(C.c_int32(world), C.c_uint64(min_bytes), C.byref(v)))
+    return int(v.value)
+
+
+def mc_create(world: int, padded_bytes: int):
+    """Rank 0: the multicast object and a POSIX fd of it to hand to the other ranks (SCM_RIGHTS)."""
+    h, fd = C.c_uint64(0), C.c_int32(-1)
+    check(load().avc_mc_create(C.c_int32(world), C.c_uint64(padded_bytes), C.byref(h), C.byref(fd)))
+    return int(h.value), int(fd.value)
+
+
+def mc_import(fd: int) -> int:
+    h = C.c_uint64(0)
+    check(load().avc_mc_import(C.c_int32(fd), C.byref(h)))
+    return int(h.value)
+
+
+def mc_add_device(handle: int) -> None:
+    check(load().avc_mc_add_device(C.c_uint64(handle)))
+
+
+def mc_bucket_alloc(handle: int, padded_bytes: int) -> AvcMcBucket:
+    b = AvcMcBucket()
+    check(load().avc_mc_bucket_alloc(C.c_uint64(handle), C.c_uint64(padded_bytes), C.byref(b)))
+    return b
+
+
+def mc_bucket_free(b: AvcMcBucket) -> None:
+    check(load().avc_mc_bucket_free(C.byref(b)))
 
 
 def comm_flag_bytes() -> int:

@@ -18,7 +18,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libavconnector_b200.so"
-SOURCES = ["avc_capi.cu", "gather.cu", "proj_gemm.cu", "splice.cu", "elementwise.cu"]
+SOURCES = ["avc_capi.cu", "avc_mc.cu", "gather.cu", "proj_gemm.cu", "splice.cu", "elementwise.cu"]
 HEADERS = [CSRC / "avc_kernels.h", CSRC / "avc_ptx.cuh", PKG_DIR.parent / "include" / "avconnector_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -112,6 +112,9 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 extern "C" {
 
+// used by the other translation units of the library (avc_mc.cu) to record the thread-local error message
+__attribute__((visibility("hidden"))) int avc_set_error_(int code, const char* msg) { return fail(code, "%s", msg); }
+
 int avc_abi_version(void) { return AVC_ABI_VERSION; }
 
 const char* avc_last_error(void) { return g_err; }
@@ -267,8 +270,13 @@ static int fill_comm(const avc_comm* c, const float* extra0, int64_t extra0_len,
   out->world = c->world;
   out->rank = c->rank;
   out->epoch = c->epoch;
+  if (c->mc_bucket != nullptr && (reinterpret_cast<uintptr_t>(c->mc_bucket) & 15))
+    return fail(AVC_ERR_INVALID, "comm: multicast bucket pointer must be 16-byte aligned");
+  out->mc = static_cast<float*>(c->mc_bucket);
   for (int p = 0; p < c->world; ++p) {
-    if (c->bucket[p] == nullptr || c->flags[p] == nullptr)
+    // with a multicast bucket the peers' copies are reached through it: only the local bucket has to be mapped
+    const bool need_bucket = c->mc_bucket == nullptr || p == c->rank;
+    if ((need_bucket && c->bucket[p] == nullptr) || c->flags[p] == nullptr)
       return fail(AVC_ERR_INVALID, "comm: rank %d's bucket / flag area is not mapped", p);
     if ((reinterpret_cast<uintptr_t>(c->bucket[p]) & 15) || (reinterpret_cast<uintptr_t>(c->flags[p]) & 15))
       return fail(AVC_ERR_INVALID, "comm: bucket / flag pointers must be 16-byte aligned");

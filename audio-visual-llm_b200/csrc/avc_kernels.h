@@ -38,6 +38,8 @@ struct CommArgs {
   int rank;
   uint32_t epoch;                   // same strictly increasing number on every rank, one per launch
   float* data[COMM_MAX_WORLD];      // gradient bucket of every rank as mapped in this process (data[rank] is local)
+  float* mc;                        // optional: multicast address of all buckets (NVSwitch); then data[p != rank] is unused
+                                    //   and the tiles are reduced with multimem.ld_reduce / multimem.st
   uint32_t* flags[COMM_MAX_WORLD];  // flag area (COMM_FLAG_WORDS words) of every rank
   int64_t seg_off[2];               // float offset of output segment s (dW_s, row-major, ld = d_cols[s]) in the bucket
   int64_t extra_off[2];             // up to two flat float ranges reduced as well once every rank flagged them

@@ -240,6 +240,21 @@ __device__ __forceinline__ void st_peer_v4(float* p, const float4& v) {
                "f"(v.w)
                : "memory");
 }
+// NVSwitch multicast address: the load returns the sum of every bound GPU's word (added in the switch), the store
+// writes every bound GPU's word
+__device__ __forceinline__ float4 multimem_ld_reduce_add_v4(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_v4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
 // async-proxy (TMA) writes to global memory -> ordered before this thread's later generic-proxy release
 __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");

@@ -136,11 +136,41 @@ __device__ __forceinline__ void comm_reduce_rows(const CommArgs& cm, int64_t bas
   }
 }
 
+// The same reduction through a multicast mapping of all ranks' buckets: one multimem.ld_reduce per vector returns the sum
+// over the ranks (added inside the NVSwitch), one multimem.st writes it to every rank.  Per GPU and direction this moves
+// (1 + 1 / world) x the bucket instead of 2 (world - 1) / world x with peer loads and stores.
+__device__ __forceinline__ void comm_reduce_rows_mc(const CommArgs& cm, int64_t base, int ld, int rows, int nvec,
+                                                    int lane) {
+  constexpr int C = 8;
+  const int total = rows * nvec;
+  for (int v0 = 0; v0 < total; v0 += 32 * C) {
+    float4 x[C];
+    int64_t off[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int v = v0 + c * 32 + lane;
+      off[c] = -1;
+      if (v < total) {
+        const int r = v / nvec;
+        off[c] = base + static_cast<int64_t>(r) * ld + 4 * (v - r * nvec);
+        x[c] = multimem_ld_reduce_add_v4(cm.mc + off[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (off[c] >= 0) multimem_st_v4(cm.mc + off[c], x[c]);
+  }
+}
+
 // COMM template parameter of the kernel: 0 = plain GEMM; 1 / 2 / 4 / 8 = fused all-reduce specialised for that world
 // size; -1 = fused all-reduce for any world size <= COMM_MAX_WORLD (peer loops predicated at run time).
+// COMM == COMM_MC: any world size, data through the multicast mapping (a separate instantiation: the kernel's register
+// count must stay low enough for the bias-sum kernel's CTAs to fit next to the GEMM CTAs, see launch_cg).
+constexpr int COMM_MC = -2;
 template <int COMM>
 __device__ __forceinline__ void comm_reduce(const CommArgs& cm, int64_t base, int ld, int rows, int nvec, int lane) {
-  if constexpr (COMM > 0) comm_reduce_rows<COMM, false>(cm, base, ld, rows, nvec, lane);
+  if constexpr (COMM == COMM_MC) comm_reduce_rows_mc(cm, base, ld, rows, nvec, lane);
+  else if constexpr (COMM > 0) comm_reduce_rows<COMM, false>(cm, base, ld, rows, nvec, lane);
   else comm_reduce_rows<COMM_MAX_WORLD, true>(cm, base, ld, rows, nvec, lane);
 }
 
@@ -657,6 +687,7 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
   };
   if constexpr (CG == 2) {
     if (comm) {
+      if (args.comm.mc != nullptr) return run(gemm_kernel<GEMM_NT, true, CG, MT, COMM_MC>);
       switch (args.comm.world) {
         case 1: return run(gemm_kernel<GEMM_NT, true, CG, MT, 1>);
         case 2: return run(gemm_kernel<GEMM_NT, true, CG, MT, 2>);

@@ -86,8 +86,12 @@ class ConnectorStep:
         if fused_allreduce and ddp and dist.get_world_size(process_group) > L.COMM_MAX_WORLD:
             fused_allreduce = False  # the flag layout holds COMM_MAX_WORLD ranks; larger jobs all-reduce through NCCL
         self.fused_allreduce = bool(fused_allreduce)
+        # AVC_COMM_MULTIMEM=1: reduce through an NVSwitch multicast mapping of the buckets (multimem.ld_reduce / st)
+        # instead of peer loads / stores.  Opt-in this round: verified on 2 GPUs only (profiles/README.md).
+        multimem = self.fused_allreduce and os.environ.get("AVC_COMM_MULTIMEM", "0") == "1"
         try:
-            self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce)
+            self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce,
+                                     multimem=multimem)
         except L.ConnectorError as e:
             if not (self.fused_allreduce and ddp):
                 raise

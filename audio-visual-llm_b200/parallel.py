@@ -9,11 +9,62 @@ Rank-local work (gather / GEMMs / splice) never communicates.
 """
 from __future__ import annotations
 
+import os
+import socket
+import tempfile
+import threading
+import time
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def _fd_socket_path(tag: str) -> str:
+    return os.path.join(tempfile.gettempdir(), f"avc_{tag}_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}.sock")
+
+
+def _serve_fd(fd: int, nclients: int, tag: str) -> threading.Thread:
+    """Hand a file descriptor to `nclients` local processes over an AF_UNIX socket (SCM_RIGHTS)."""
+    path = _fd_socket_path(tag)
+    if os.path.exists(path):
+        os.unlink(path)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(max(1, nclients))
+
+    def run():
+        try:
+            for _ in range(nclients):
+                conn, _ = srv.accept()
+                socket.send_fds(conn, [b"fd"], [fd])
+                conn.close()
+        finally:
+            srv.close()
+            if os.path.exists(path):
+                os.unlink(path)
+
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    return t
+
+
+def _fetch_fd(tag: str, timeout_s: float = 30.0) -> int:
+    path = _fd_socket_path(tag)
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    deadline = time.time() + timeout_s
+    while True:
+        try:
+            c.connect(path)
+            break
+        except (ConnectionRefusedError, FileNotFoundError):
+            if time.time() > deadline:
+                raise TimeoutError(f"no fd server at {path}")
+            time.sleep(0.01)
+    _, fds, _, _ = socket.recv_fds(c, 16, 1)
+    c.close()
+    return fds[0]
 
 
 class PeerMemory:
@@ -24,7 +75,10 @@ class PeerMemory:
 
     `next_epoch()` must be called once per fused launch, in the same order on every rank."""
 
-    def __init__(self, nfloats: int, device, process_group=None, timeout_s: float = 20.0):
+    def __init__(self, nfloats: int, device, process_group=None, timeout_s: float = 20.0, multimem: bool = False):
+        """multimem=True: the bucket is bound to an NVSwitch multicast object (`avc_mc_*`), and the fused launch reduces
+        with multimem.ld_reduce / multimem.st instead of peer loads / stores (falls back to the peer mapping, on every
+        rank alike, when the devices do not support multicast)."""
         from . import _lib as L
 
         self._L = L
@@ -36,9 +90,19 @@ class PeerMemory:
         if self.world > L.COMM_MAX_WORLD:
             raise L.ConnectorError(f"peer-memory all-reduce supports up to {L.COMM_MAX_WORLD} ranks, got {self.world}")
         self.nfloats = nfloats
+        self.mc = None  # AvcMcBucket when the multicast transport is in use
+        if multimem:
+            ok = torch.tensor([1 if L.mc_supported(self.device.index or 0) else 0], dtype=torch.int32, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            multimem = bool(int(ok.item()))
         with torch.cuda.device(self.device):
-            self._own = (L.comm_alloc(nfloats * 4), L.comm_alloc(L.comm_flag_bytes()))
-            mine = (L.comm_export(self._own[0]), L.comm_export(self._own[1]))
+            if multimem:
+                self.mc = self._setup_multicast(L, nfloats * 4, process_group)
+            self._own = (self.mc.ptr if self.mc is not None else L.comm_alloc(nfloats * 4),
+                         L.comm_alloc(L.comm_flag_bytes()))
+            # multicast transport: the peers' buckets are reached through the multicast address, only flags are mapped
+            mine = (None if self.mc is not None else L.comm_export(self._own[0]), L.comm_export(self._own[1]))
             handles = [mine]
             if self.world > 1:
                 handles = [None] * self.world
@@ -50,8 +114,10 @@ class PeerMemory:
                     if r == self.rank:
                         pb, pf = self._own
                     else:
-                        pb = L.comm_open(hb)
-                        self._opened.append(pb)
+                        pb = 0
+                        if hb is not None:
+                            pb = L.comm_open(hb)
+                            self._opened.append(pb)
                         pf = L.comm_open(hf)
                         self._opened.append(pf)
                     self.bucket_ptrs.append(pb)
@@ -67,9 +133,8 @@ class PeerMemory:
             if err is not None:
                 for p in self._opened:
                     L.comm_close(p)
-                for p in self._own:
-                    L.comm_free(p)
-                self._opened, self._own = [], None
+                self._free_own()
+                self._opened = []
                 raise L.ConnectorError(f"peer-memory setup failed on rank {self.rank}: {err}")
         self.flat = L.as_tensor(self._own[0], nfloats, torch.float32, self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -85,6 +150,42 @@ class PeerMemory:
         if self.world > 1:
             dist.barrier(group=process_group)  # every rank has mapped every block before the first launch
 
+    def _setup_multicast(self, L, nbytes: int, group):
+        """rank 0 creates the multicast object and serves its fd; every rank adds its device, allocates + binds."""
+        padded = L.mc_padded_bytes(self.world, nbytes)
+        tag = "mc"
+        if self.rank == 0:
+            handle, fd = L.mc_create(self.world, padded)
+            server = _serve_fd(fd, self.world - 1, tag)
+            if self.world > 1:
+                dist.barrier(group=group)
+            server.join()
+            os.close(fd)
+        else:
+            dist.barrier(group=group)
+            fd = _fetch_fd(tag)
+            handle = L.mc_import(fd)
+            os.close(fd)
+        L.mc_add_device(handle)
+        if self.world > 1:
+            dist.barrier(group=group)  # every device is in the object before anyone binds memory to it
+        b = L.mc_bucket_alloc(handle, padded)
+        if self.world > 1:
+            dist.barrier(group=group)  # every rank's memory is bound before the first multimem access
+        return b
+
+    def _free_own(self):
+        L = self._L
+        if self._own is None:
+            return
+        if self.mc is not None:
+            L.mc_bucket_free(self.mc)
+            self.mc = None
+        else:
+            L.comm_free(self._own[0])
+        L.comm_free(self._own[1])
+        self._own = None
+
     def next_epoch(self):
         """Descriptor of the next fused launch (the epoch number is the protocol's only per-step state)."""
         L = self._L
@@ -92,8 +193,9 @@ class PeerMemory:
         c = L.AvcComm()
         c.world, c.rank, c.epoch = self.world, self.rank, self.epoch
         for r in range(self.world):
-            c.bucket[r] = self.bucket_ptrs[r]
+            c.bucket[r] = self.bucket_ptrs[r] or None
             c.flags[r] = self.flag_ptrs[r]
+        c.mc_bucket = self.mc.mc_ptr if self.mc is not None else None
         c.status = self.status.data_ptr()
         c.timeout_ns = self.timeout_ns
         c.bucket_bytes = self.nfloats * 4
@@ -117,9 +219,8 @@ class PeerMemory:
             for p in self._opened:
                 L.comm_close(p)
             self.flat = None
-            for p in self._own:
-                L.comm_free(p)
-        self._opened, self._own = [], None
+            self._free_own()
+        self._opened = []
 
 
 class GradBucket:
@@ -128,7 +229,7 @@ class GradBucket:
     peer=True puts the buffer in `PeerMemory` so that the dW GEMM can all-reduce it itself (`self.peer`)."""
 
     def __init__(self, shapes: Dict[str, Tuple[int, ...]], device, process_group=None, align_elems: int = 64,
-                 peer: bool = False):
+                 peer: bool = False, multimem: bool = False):
         self.views: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         offs, total = {}, 0
         for name, shape in shapes.items():
@@ -137,7 +238,7 @@ class GradBucket:
                 n *= d
             offs[name] = (total, n, shape)
             total += (n + align_elems - 1) // align_elems * align_elems  # keep every view 256-byte aligned
-        self.peer: Optional[PeerMemory] = PeerMemory(total, device, process_group) if peer else None
+        self.peer: Optional[PeerMemory] = PeerMemory(total, device, process_group, multimem=multimem) if peer else None
         self.flat = self.peer.flat if peer else torch.zeros(total, dtype=torch.float32, device=device)
         self._pads = []
         for name, (o, n, shape) in offs.items():

@@ -126,6 +126,9 @@ typedef struct avc_comm {
   int32_t* status;                   /* local device int32, zero-initialised */
   uint64_t timeout_ns;               /* 0 = 20 s */
   uint64_t bucket_bytes;             /* size of every rank's bucket (ranges passed to the calls are checked against it) */
+  void* mc_bucket;                   /* optional (NULL: peer loads / stores): multicast address of all ranks' buckets from
+                                        avc_mc_bucket_alloc; the launch then reduces with multimem.ld_reduce (summed in
+                                        the NVSwitch) and multimem.st, and bucket[p] is only needed for p == rank */
 } avc_comm;
 AVC_API size_t avc_comm_flag_bytes(void);
 /* cudaMalloc + zero-fill on the current device (IPC-exportable, unlike pooled allocator blocks). */
@@ -143,6 +146,30 @@ AVC_API int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, in
                                       int64_t extra1_len, int32_t max_sms, void* stream);
 /* Enqueue after the kernel that wrote this rank's extra ranges (same stream): flags them ready for comm->epoch. */
 AVC_API int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extra1_len, void* stream);
+
+/* ---- multicast bucket (NVSwitch "NVLS"): optional transport of the fused all-reduce --------------------------------
+ * Every rank's gradient bucket is bound at the same offset of ONE multicast object, so that a multimem.ld_reduce on
+ * mc_ptr + x returns the sum of all ranks' words at x (added inside the switch) and a multimem.st writes all of them.
+ * Setup (one process per GPU; the fd travels between processes over an AF_UNIX socket with SCM_RIGHTS):
+ *   all ranks   avc_mc_padded_bytes(world, bytes) -> size rounded to the multicast granularity (512 MiB on B200)
+ *   rank 0      avc_mc_create -> object handle + POSIX fd          other ranks  avc_mc_import(fd)
+ *   all ranks   avc_mc_add_device (current device); BARRIER; avc_mc_bucket_alloc (cuMemCreate + bind + map, zero-filled);
+ *               BARRIER before first use.  avc_comm.bucket[rank] = ptr, avc_comm.mc_bucket = mc_ptr.
+ * avc_mc_supported: 1 iff the device and driver support multicast objects (NVSwitch systems). */
+typedef struct avc_mc_bucket {
+  void* ptr;             /* this rank's bucket (ordinary device address) */
+  void* mc_ptr;          /* multicast address of every rank's bucket (multimem.* instructions only) */
+  uint64_t bytes;        /* padded size */
+  uint64_t mem_handle;   /* driver handles, released by avc_mc_bucket_free */
+  uint64_t mc_handle;
+} avc_mc_bucket;
+AVC_API int avc_mc_supported(int32_t device, int32_t* supported);
+AVC_API int avc_mc_padded_bytes(int32_t world, uint64_t min_bytes, uint64_t* padded_bytes);
+AVC_API int avc_mc_create(int32_t world, uint64_t padded_bytes, uint64_t* mc_handle, int32_t* fd);
+AVC_API int avc_mc_import(int32_t fd, uint64_t* mc_handle);
+AVC_API int avc_mc_add_device(uint64_t mc_handle);
+AVC_API int avc_mc_bucket_alloc(uint64_t mc_handle, uint64_t padded_bytes, avc_mc_bucket* out);
+AVC_API int avc_mc_bucket_free(avc_mc_bucket* b);
 
 /* ---- bias gradient: deterministic column sum over flagged rows (one launch, fixed summation tree) -------------
  * out_i[c] = alpha_i * sum_{b, r < sum_rows : flag_i(b, r)} dY[b, dy_row_base + r, c]      (db = sum dY)

@@ -33,7 +33,8 @@ plan = pkg.FusePlan(fusion="concat", audio_stride=4, video_stride=2, max_seq_len
 ref = ConnectorStep(shape, plan, dev, seed=10, fused_allreduce=False)  # rank 0's parameters everywhere
 
 
-def make(fused, overlap=False):
+def make(fused, overlap=False, multimem=False):
+    os.environ["AVC_COMM_MULTIMEM"] = "1" if multimem else "0"
     eng = ConnectorStep(shape, plan, dev, seed=10 + rank, fused_allreduce=fused)  # different data per rank
     for n in ("wa", "wv", "ba", "bv"):
         getattr(eng, n).copy_(getattr(ref, n))
@@ -49,8 +50,13 @@ dist.all_gather(gathered, local_only.bucket.flat)
 mean = torch.stack(gathered).double().mean(0)
 del gathered
 res = {}
-for name, fused, overlap in (("fused", True, False), ("nccl", False, False), ("overlap", False, True)):
-    eng = make(fused, overlap)
+variants = [("fused", True, False, False), ("nccl", False, False, False), ("overlap", False, True, False)]
+if "--multimem" in sys.argv:  # the fused launch reducing through an NVSwitch multicast mapping (multimem.ld_reduce / st)
+    variants.insert(1, ("fused_multimem", True, False, True))
+for name, fused, overlap, mm in variants:
+    eng = make(fused, overlap, mm)
+    if mm and rank == 0:
+        print(f"dp_check {name}: multicast transport active = {eng.bucket.peer.mc is not None}", file=sys.stderr)
     for _ in range(3):      # several epochs: flags are never reset between launches
         eng.bucket.flat.fill_(float("nan"))
         eng.bucket.zero_padding()
@@ -84,7 +90,7 @@ for name, fused, overlap in (("fused", True, False), ("nccl", False, False), ("o
     del eng
     torch.cuda.empty_cache()
 scale = float(res["nccl"].abs().max())
-for a in ("fused", "overlap"):
+for a in [v[0] for v in variants if v[0] != "nccl"]:
     assert float((res[a] - res["nccl"]).abs().max()) <= 1e-6 * scale, a
 if rank == 0:
     print("dp_check ok: world", world)
