@@ -86,9 +86,13 @@ class ConnectorStep:
         if fused_allreduce and ddp and dist.get_world_size(process_group) > L.COMM_MAX_WORLD:
             fused_allreduce = False  # the flag layout holds COMM_MAX_WORLD ranks; larger jobs all-reduce through NCCL
         self.fused_allreduce = bool(fused_allreduce)
-        # AVC_COMM_MULTIMEM=1: reduce through an NVSwitch multicast mapping of the buckets (multimem.ld_reduce / st)
-        # instead of peer loads / stores.  Opt-in this round: verified on 2 GPUs only (profiles/README.md).
-        multimem = self.fused_allreduce and os.environ.get("AVC_COMM_MULTIMEM", "0") == "1"
+        # Transport of the fused all-reduce: an NVSwitch multicast mapping of the buckets (multimem.ld_reduce adds in the
+        # switch, multimem.st writes every rank) instead of peer loads / stores.  Default for <= 4 ranks, where it was
+        # verified and measured this round (N = 4: 0.96 vs 1.02 ms / step); AVC_COMM_MULTIMEM=1 / 0 forces it on / off.
+        # Falls back to the peer mapping, on all ranks alike, when multicast objects are not available.
+        world_ = dist.get_world_size(process_group) if ddp else 1
+        multimem = self.fused_allreduce and \
+            os.environ.get("AVC_COMM_MULTIMEM", "1" if world_ <= 4 else "0") == "1"
         try:
             self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce,
                                      multimem=multimem)

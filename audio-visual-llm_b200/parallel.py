@@ -151,27 +151,57 @@ class PeerMemory:
             dist.barrier(group=process_group)  # every rank has mapped every block before the first launch
 
     def _setup_multicast(self, L, nbytes: int, group):
-        """rank 0 creates the multicast object and serves its fd; every rank adds its device, allocates + binds."""
-        padded = L.mc_padded_bytes(self.world, nbytes)
-        tag = "mc"
+        """rank 0 creates the multicast object and serves its fd; every rank adds its device, allocates + binds.
+        Every stage ends with an agreement (all-reduce MIN of "it worked here"), which is also the barrier the driver
+        API needs between the stages; if any rank fails, ALL ranks return None and use the peer mapping instead."""
+
+        def agree(ok: bool) -> bool:
+            if self.world == 1:
+                return ok
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
+        def attempt(fn):
+            try:
+                return fn(), None
+            except (L.ConnectorError, OSError, TimeoutError) as e:
+                return None, e
+
+        padded, err = attempt(lambda: L.mc_padded_bytes(self.world, nbytes))
+        created, fd = None, -1
+        if err is None and self.rank == 0:
+            created, err = attempt(lambda: L.mc_create(self.world, padded))
+        if not agree(err is None):
+            return None
+        handle = None
         if self.rank == 0:
-            handle, fd = L.mc_create(self.world, padded)
-            server = _serve_fd(fd, self.world - 1, tag)
-            if self.world > 1:
-                dist.barrier(group=group)
-            server.join()
+            handle, fd = created
+            server = _serve_fd(fd, self.world - 1, "mc")
+            agree(True)                      # the socket is listening
+            server.join(timeout=60)
             os.close(fd)
         else:
-            dist.barrier(group=group)
-            fd = _fetch_fd(tag)
-            handle = L.mc_import(fd)
-            os.close(fd)
-        L.mc_add_device(handle)
-        if self.world > 1:
-            dist.barrier(group=group)  # every device is in the object before anyone binds memory to it
-        b = L.mc_bucket_alloc(handle, padded)
-        if self.world > 1:
-            dist.barrier(group=group)  # every rank's memory is bound before the first multimem access
+            agree(True)
+
+            def imp():
+                f = _fetch_fd("mc")
+                try:
+                    return L.mc_import(f)
+                finally:
+                    os.close(f)
+
+            handle, err = attempt(imp)
+        if not agree(err is None):
+            return None
+        _, err = attempt(lambda: L.mc_add_device(handle))
+        if not agree(err is None):           # every device is in the object before anyone binds memory to it
+            return None
+        b, err = attempt(lambda: L.mc_bucket_alloc(handle, padded))
+        if not agree(err is None):           # every rank's memory is bound before the first multimem access
+            if b is not None:
+                L.mc_bucket_free(b)
+            return None
         return b
 
     def _free_own(self):

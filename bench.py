@@ -334,9 +334,11 @@ def main():
     if world == 1:
         collective = "none"
     elif eng.fused_allreduce:
-        collective = ("projector-grad all-reduce fused into the dW GEMM launch (100.7 MB fp32 flat bucket in peer-mapped "
-                      "memory: comm warps of the GEMM CTAs sum finished tiles over NVLink with peer loads / stores "
-                      "while later tiles are computed)")
+        mc = eng.bucket.peer is not None and eng.bucket.peer.mc is not None
+        collective = ("projector-grad all-reduce fused into the dW GEMM launch (100.7 MB fp32 flat bucket; comm warps of "
+                      "the GEMM CTAs reduce finished tiles over NVLink while later tiles are computed; transport: " +
+                      ("NVSwitch multicast mapping, multimem.ld_reduce + multimem.st)" if mc
+                       else "peer-mapped memory (CUDA IPC), peer loads + peer stores)"))
     else:
         collective = ("projector-grad all-reduce (NCCL sum of pre-scaled grads, 100.7 MB fp32 flat bucket; " +
                       ("audio-weight span overlapped with the video-weight dW launch)" if eng.overlap_comm

@@ -76,6 +76,12 @@ The same step with one NCCL all-reduce after the backward (`AVC_FUSED_ALLREDUCE=
 |---|---|---|---|---|
 """ + "\n".join(nccl) + """
 
+Transport of the fused all-reduce (`r01_mc_probe_n2.log`, `r01_dp_check_n2_multimem.log`, `r01_dp_check_n4_multimem.log`;
+30-step runs of `tools/dp_check.py --big --multimem` on one box each): binding the buckets to an NVSwitch multicast object
+and reducing with `multimem.ld_reduce` / `multimem.st` instead of peer loads / stores gives 0.958 vs 1.023 ms / step at
+N = 4 and 0.977 vs 0.988 ms at N = 2 (NCCL schedule on that N = 2 box: 1.122 ms).  Default for <= 4 ranks from here on;
+the N = 2 / 4 rows of the table above were taken before that, with the peer transport.  Not yet run at N = 8.
+
 `r01_dp_check_n8.log`, `r01_dp_check_n2_cfg2.log`: `tools/dp_check.py` under torchrun -- the fused, NCCL and overlapped
 schedules give the same reduced gradients (<= 1.3e-7 of an fp64 mean) and every rank ends with bit-identical buckets.
 e2e at N > 1 moves 147.6 MB per GPU per step from pinned host memory and is PCIe-bound per GPU.
@@ -124,8 +130,8 @@ e2e at N > 1 moves 147.6 MB per GPU per step from pinned host memory and is PCIe
    the all-reduce INTO the dW GEMM (comm warps + peer loads / stores, no SMs given up) is: 1.05 vs 1.17 ms / step at
    N = 2, 1.13 vs 1.31 ms at N = 8 (+16 % throughput).  At N = 8 the fused launch (0.65 ms against 0.43 ms for the plain
    dW) is bound by the peer traffic of the pull-then-push scheme (176 MB per direction per GPU, ~350 GB/s effective);
-   next: push-only transport (TMA stores of partial tiles straight into the owner's staging area) or NVLS
-   `multimem.ld_reduce` / `multimem.st`, which moves 100 MB per direction.
+   the NVSwitch multicast transport (`multimem.ld_reduce` / `multimem.st`, 113 MB per direction) is in the tree,
+   verified and faster at N = 2 / 4, and still has to be run at N = 8.
 6. CUDA loads kernels lazily, and loading one can wait for running kernels: the first fused launch spun for its whole
    20 s timeout waiting for a bias-sum kernel that could not be loaded while it ran -> the kernels launched next to a
    waiting GEMM are preloaded (`avc_comm_alloc`).
