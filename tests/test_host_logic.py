@@ -147,3 +147,31 @@ def test_optimizer_decay_groups_follow_the_reference(avc):
 
     assert ConnectorAdamW.decay_for(type("X", (), {"weight_decay": 0.01})(), "audio_connector.linear.bias") == 0.0
     assert ConnectorAdamW.decay_for(type("X", (), {"weight_decay": 0.01})(), "video_connector.linear.weight") == 0.01
+
+
+def test_fd_passing_between_threads(tmp_path, monkeypatch):
+    """The multicast object's POSIX fd travels from rank 0 to the other ranks over an AF_UNIX socket (SCM_RIGHTS):
+    `parallel._serve_fd` / `_fetch_fd`.  Checked here with an ordinary file: the received descriptor is a NEW number
+    that refers to the same open file."""
+    import os
+    import tempfile
+
+    from audio_visual_llm_b200 import parallel
+
+    monkeypatch.setenv("MASTER_PORT", str(40000 + os.getpid() % 20000))
+    monkeypatch.setattr(tempfile, "tempdir", str(tmp_path))
+    payload = tmp_path / "payload.bin"
+    payload.write_bytes(b"multicast-object")
+    fd = os.open(payload, os.O_RDONLY)
+    try:
+        server = parallel._serve_fd(fd, 2, "test")
+        got = [parallel._fetch_fd("test", timeout_s=5.0) for _ in range(2)]
+        server.join(timeout=5)
+        assert not server.is_alive()
+        for g in got:
+            assert g != fd
+            assert os.pread(g, 64, 0) == b"multicast-object"
+            os.close(g)
+        assert not os.path.exists(parallel._fd_socket_path("test")), "the server removes its socket"
+    finally:
+        os.close(fd)
