@@ -6,9 +6,9 @@ fwd + bwd, with every buffer pre-allocated (no allocator traffic, CUDA-graph fri
 
 This is the same kernel sequence `connector_ops._FusedConnectorFn` runs under autograd; the engine exists so
 the data-parallel trainer (and bench.py) can drive it without per-step Python allocation.  The projector
-gradients land in ONE flat fp32 bucket ([dWa | dWv | dba | dbv]) so the only collective of the path -- the
-all-reduce the trainer needs between backward() and clip_grad_norm_ (clip_whisper_trainer.py:454-458) -- is a
-single NCCL call.
+gradients land in ONE flat fp32 bucket ([dWa | dWv | dba | dbv]); the only collective of the path -- the
+all-reduce the trainer needs between backward() and clip_grad_norm_ (clip_whisper_trainer.py:454-458) -- runs inside
+the dW GEMM launch over peer-mapped / multicast memory (`_backward_fused_allreduce`), or as one NCCL call after it.
 """
 from __future__ import annotations
 

@@ -2,10 +2,15 @@
 
 The path has exactly one collective: all-reduce(mean) of the projector gradients between
 backward() and the trainer's clip_grad_norm_ (clip_whisper_trainer.py:454-458).  The reference has no
-distributed code at all, so this is new.  All gradients live in ONE flat fp32 bucket so the collective is a
-single NCCL call (~100 MB at Llama-2-7B width: latency- not link-bound over NVSwitch); the dW GEMM and the bias
-column-sum kernels write straight into views of the bucket, so there is no flatten/unflatten copy.
-Rank-local work (gather / GEMMs / splice) never communicates.
+distributed code at all, so this is new.  All gradients live in ONE flat fp32 bucket (~100 MB at Llama-2-7B width);
+the dW GEMM and the bias column-sum kernels write straight into views of the bucket, so there is no flatten /
+unflatten copy.  Rank-local work (gather / GEMMs / splice) never communicates.
+
+Two ways to reduce the bucket:
+  * `PeerMemory` (default on NCCL process groups of <= 8 ranks): the bucket lives in memory every rank's process maps
+    -- CUDA IPC peer mappings, or an NVSwitch multicast object -- and the dW GEMM launch all-reduces it itself
+    (`avc_proj_bwd_dw_allreduce`); torch.distributed only carries handles, agreements and barriers during setup.
+  * `GradBucket.allreduce()`: one NCCL (or gloo, for the CPU tests) all-reduce after the backward.
 """
 from __future__ import annotations
 
