@@ -14,7 +14,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libavconnector_b200.so"
 _lib: Optional[C.CDLL] = None
 
-AVC_ABI_VERSION = 1
+AVC_ABI_VERSION = 2
 EXPORTS = (
     "avc_abi_version", "avc_last_error", "avc_device_check", "avc_gather_fwd", "avc_proj_fwd",
     "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",

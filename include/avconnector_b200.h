@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AVC_ABI_VERSION 1
+#define AVC_ABI_VERSION 2  /* 2: colsum workspace header contract, avc_comm_* / avc_mc_* data-parallel entry points */
 
 enum avc_status {
   AVC_OK = 0,

@@ -87,4 +87,4 @@ def test_plain_c_program_links_against_the_abi(avc, tmp_path):
                         "-L", str(lib_dir), "-lavconnector_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0 and "abi=1" in out.stdout and "device_check=" in out.stdout
+    assert out.returncode == 0 and "abi=2" in out.stdout and "device_check=" in out.stdout
