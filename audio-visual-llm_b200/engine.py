@@ -147,6 +147,7 @@ class ConnectorStep:
         npack = int(self.use_a) + int(self.use_v)
         self.launches_per_step = npack + (3 if self.direct else 5) + 1  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
+        self.nvtx = os.environ.get("AVC_NVTX", "0") == "1"
         # N > 1: optionally all-reduce the audio-weight span while the video-weight dW launch still runs.  Measured on
         # B200 x8 (profiles/README.md): NCCL needs ~48+ SMs to run at speed, which the persistent GEMM must give up, so
         # the overlapped schedule is no faster than one all-reduce after the backward (1.32 ms either way at N = 8,
@@ -182,6 +183,16 @@ class ConnectorStep:
         self.events = {n: [] for n in names}
 
     def _timed(self, name, fn):
+        if self.nvtx:  # AVC_NVTX=1: one NVTX range per launch, for `ncu --nvtx --nvtx-include "proj_fwd/"` and timelines
+            torch.cuda.nvtx.range_push(name)
+            try:
+                self._timed_inner(name, fn)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        else:
+            self._timed_inner(name, fn)
+
+    def _timed_inner(self, name, fn):
         if self.events is None or name not in self.events:
             fn()
             return
