@@ -7,7 +7,7 @@
 // frame stride of (1+Np)*Dv also folds in the CLS-row select of clip_whisper_model.py:1141-1142.
 //
 // Data never touches registers: each warp runs a ring of smem stages; one elected lane issues
-// cp.async.bulk (TMA, global->smem, mbarrier complete_tx) loads two items ahead and
+// cp.async.bulk (TMA, global->smem, mbarrier complete_tx) loads G_LOOKAHEAD items ahead and
 // cp.async.bulk (smem->global, bulk_group) stores behind.  Padding comes from a zeroed smem block.
 #include "avc_kernels.h"
 #include "avc_ptx.cuh"
