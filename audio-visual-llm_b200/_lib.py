@@ -14,7 +14,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libavconnector_b200.so"
 _lib: Optional[C.CDLL] = None
 
-AVC_ABI_VERSION = 2
+AVC_ABI_VERSION = 3
 EXPORTS = (
     "avc_abi_version", "avc_last_error", "avc_device_check", "avc_gather_fwd", "avc_proj_fwd",
     "avc_proj_bwd_dw", "avc_colsum_workspace_bytes", "avc_colsum", "avc_pack_weight", "avc_splice_fwd",
@@ -24,7 +24,19 @@ EXPORTS = (
     "avc_proj_bwd_dw_allreduce", "avc_comm_signal_extra", "avc_colsum_comm", "avc_colsum_workspace_header_bytes",
     "avc_mc_supported", "avc_mc_padded_bytes", "avc_mc_create", "avc_mc_import", "avc_mc_add_device",
     "avc_mc_bucket_alloc", "avc_mc_bucket_free",
+    "avc_proj_bwd_dw_db", "avc_proj_bwd_dw_db_allreduce", "avc_proj_bwd_dx", "avc_gather_bwd", "avc_cast_bf16",
 )
+
+# AVC_DTYPE_* codes of include/avconnector_b200.h
+DTYPE_CODES = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
+BIAS_COLS = 64  # columns of the token-present operand of the bias work items (avc_bias_grad.present)
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return DTYPE_CODES[dt]
+    except KeyError:
+        raise ConnectorError(f"dtype {dt} is not supported by the B200 connector (bf16, fp16 or fp32)") from None
 
 
 class AvcFeat(C.Structure):
@@ -62,6 +74,11 @@ class AvcComm(C.Structure):
         ("bucket", C.c_void_p * COMM_MAX_WORLD), ("flags", C.c_void_p * COMM_MAX_WORLD), ("status", C.c_void_p),
         ("timeout_ns", C.c_uint64), ("bucket_bytes", C.c_uint64), ("mc_bucket", C.c_void_p),
     ]
+
+
+class AvcBiasGrad(C.Structure):
+    _fields_ = [("present", C.POINTER(AvcMat)), ("out0", C.c_void_p), ("out1", C.c_void_p), ("alpha0", C.c_float),
+                ("alpha1", C.c_float)]
 
 
 class AvcMcBucket(C.Structure):
@@ -168,17 +185,90 @@ def proj_fwd(a_segs: Sequence[torch.Tensor], w_segs: Sequence[torch.Tensor], y: 
              act: int = 0, bias_scale0: float = 1.0, bias_scale1: float = 1.0) -> None:
     check(load().avc_proj_fwd(
         C.c_int32(len(a_segs)), _mat_array([mat(t) for t in a_segs]), _mat_array([mat(t) for t in w_segs]),
-        C.byref(mat(y)), C.c_int32(1 if y.dtype == torch.float32 else 0), C.c_void_p(_ptr(bias0)),
+        C.byref(mat(y)), C.c_int32(dtype_code(y.dtype)), C.c_void_p(_ptr(bias0)),
         C.c_void_p(_ptr(bias1)), C.c_float(bias_scale0), C.c_float(bias_scale1), C.c_void_p(_ptr(row_flags)),
         C.c_int32(flag_rows0), C.c_int32(flag_rows1), C.c_int32(act), stream_ptr()))
 
 
+_PRESENT_CACHE: dict = {}
+
+
+def present_operand(batch: int, rows: int, device, row_flags: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token-present operand of the bias work items (`avc_bias_grad.present`): bf16 [batch, rows, 64] whose column
+    0 / 1 is 1 where the row carries an audio / video token.  Dense streams: all ones (a cached constant);
+    `row_flags` (uint8 [batch * rows], bit 0 / 1 as written by `avc_gather_fwd`): per-row bits."""
+    device = torch.device(device)
+    if row_flags is None:
+        key = (batch, rows, device)
+        f = _PRESENT_CACHE.get(key)
+        if f is None:
+            f = torch.zeros(batch, rows, BIAS_COLS, dtype=torch.bfloat16, device=device)
+            f[:, :, :2] = 1
+            if len(_PRESENT_CACHE) >= 8:
+                _PRESENT_CACHE.pop(next(iter(_PRESENT_CACHE)))
+            _PRESENT_CACHE[key] = f
+        return f
+    f = torch.zeros(batch, rows, BIAS_COLS, dtype=torch.bfloat16, device=device)
+    fl = row_flags.view(batch, rows)
+    f[:, :, 0] = (fl & 1).to(torch.bfloat16)
+    f[:, :, 1] = ((fl >> 1) & 1).to(torch.bfloat16)
+    return f
+
+
+def _bias_grad(present: torch.Tensor, out0: Optional[torch.Tensor], out1: Optional[torch.Tensor], alpha0: float,
+               alpha1: float):
+    if present.dtype != torch.bfloat16 or present.dim() != 3 or present.shape[2] != BIAS_COLS:
+        raise ValueError(f"token-present operand must be bf16 [batch, rows, {BIAS_COLS}]")
+    m = mat(present)
+    b = AvcBiasGrad(C.pointer(m), _ptr(out0), _ptr(out1), alpha0, alpha1)
+    b._keep = (m, present, out0, out1)
+    return b
+
+
 def proj_bwd_dw(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
-                alpha: Sequence[float], dy_row_base: int = 0, max_sms: int = 0) -> None:
+                alpha: Sequence[float], dy_row_base: int = 0, max_sms: int = 0, bias=None) -> None:
+    """bias = (present, db0, db1, alpha0, alpha1): also produce the bias gradients inside the same launch."""
     al = (C.c_float * len(x_segs))(*alpha)
-    check(load().avc_proj_bwd_dw(
+    if bias is None:
+        check(load().avc_proj_bwd_dw(
+            C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
+            _mat_array([mat(t) for t in dw_segs]), al, C.c_int32(max_sms), stream_ptr()))
+        return
+    bg = _bias_grad(*bias)
+    check(load().avc_proj_bwd_dw_db(
         C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
-        _mat_array([mat(t) for t in dw_segs]), al, C.c_int32(max_sms), stream_ptr()))
+        _mat_array([mat(t) for t in dw_segs]), al, C.byref(bg), C.c_int32(max_sms), stream_ptr()))
+
+
+def proj_bwd_dx(dy_segs: Sequence[torch.Tensor], wt_segs: Sequence[torch.Tensor], dx: torch.Tensor) -> None:
+    """dX = sum_s dY_s . W_s with wt_segs[s] = W_s^T (bf16 [K_in, H_s] from pack_weight_t)."""
+    check(load().avc_proj_bwd_dx(_mat_array([mat(t) for t in dy_segs]), C.c_int32(len(dy_segs)),
+                                 _mat_array([mat(t) for t in wt_segs]), C.byref(mat(dx)),
+                                 C.c_int32(dtype_code(dx.dtype)), stream_ptr()))
+
+
+def gather_bwd(da: torch.Tensor, col_off: int, d_feat: torch.Tensor, stack: int, repeat: int, batch: int,
+               tokens_per_sample: int, tok_offset: Optional[torch.Tensor] = None,
+               valid: Optional[torch.Tensor] = None) -> None:
+    """d_feat [B, T, D] (bf16 or fp32, dense) <- column segment [col_off, col_off + stack * D) of dA [M, K] (bf16)."""
+    if da.dtype != torch.bfloat16 or da.dim() != 2 or da.stride(1) != 1:
+        raise ValueError("dA must be a bf16 matrix with contiguous columns")
+    if d_feat.dim() != 3 or d_feat.stride(2) != 1 or d_feat.dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError("d_feat must be bf16 / fp32 [batch, frames, dim] with contiguous dim")
+    f = AvcFeat(d_feat.data_ptr(), d_feat.stride(0), d_feat.stride(1), d_feat.shape[1], d_feat.shape[2], stack, repeat,
+                _ptr(valid))
+    check(load().avc_gather_bwd(C.c_void_p(da.data_ptr()), C.c_int64(da.stride(0)), C.c_int64(col_off), C.byref(f),
+                                C.c_int32(dtype_code(d_feat.dtype)), C.c_int32(batch), C.c_void_p(_ptr(tok_offset)),
+                                C.c_int32(tokens_per_sample), stream_ptr()))
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor, alpha: float = 1.0) -> None:
+    """dst_bf16[r, c] = bf16(alpha * src[r, c]) for 2-D bf16 / fp16 / fp32 `src` (columns contiguous)."""
+    if src.dim() != 2 or dst.dim() != 2 or src.stride(1) != 1 or dst.stride(1) != 1 or dst.dtype != torch.bfloat16:
+        raise ValueError("cast_bf16 needs 2-D matrices with contiguous columns and a bf16 destination")
+    check(load().avc_cast_bf16(C.c_void_p(src.data_ptr()), C.c_int32(dtype_code(src.dtype)), C.c_int64(src.stride(0)),
+                               C.c_void_p(dst.data_ptr()), C.c_int64(dst.stride(0)), C.c_int64(src.shape[0]),
+                               C.c_int64(src.shape[1]), C.c_float(alpha), stream_ptr()))
 
 
 # ------------------------------------------------------------------------------------------ peer memory (data parallel)
@@ -271,9 +361,18 @@ def as_tensor(ptr: int, numel: int, dtype: torch.dtype, device) -> torch.Tensor:
 
 def proj_bwd_dw_allreduce(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
                           alpha: Sequence[float], comm: AvcComm, extra0: Optional[torch.Tensor] = None,
-                          extra1: Optional[torch.Tensor] = None, dy_row_base: int = 0, max_sms: int = 0) -> None:
-    """proj_bwd_dw whose launch also all-reduces (sums) the dW segments and the extra ranges over the ranks."""
+                          extra1: Optional[torch.Tensor] = None, dy_row_base: int = 0, max_sms: int = 0,
+                          bias=None) -> None:
+    """proj_bwd_dw whose launch also all-reduces (sums) the dW segments and the extra ranges over the ranks.
+    bias = (present, db0, db1, alpha0, alpha1): the launch produces the bias gradients itself (they are its extra
+    ranges; extra0 / extra1 are ignored)."""
     al = (C.c_float * len(x_segs))(*alpha)
+    if bias is not None:
+        bg = _bias_grad(*bias)
+        check(load().avc_proj_bwd_dw_db_allreduce(
+            C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
+            _mat_array([mat(t) for t in dw_segs]), al, C.byref(bg), C.byref(comm), C.c_int32(max_sms), stream_ptr()))
+        return
     check(load().avc_proj_bwd_dw_allreduce(
         C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
         _mat_array([mat(t) for t in dw_segs]), al, C.byref(comm), C.c_void_p(_ptr(extra0)),
@@ -346,9 +445,8 @@ def row_resample(x: torch.Tensor, out: torch.Tensor, row_ptr: torch.Tensor, col_
     """out[b, i, :] = sum_t weight[t] * x[b, col_idx[t], :] over CSR row i; x [B, S, H], out [B, L, H] contiguous."""
     if not (x.is_contiguous() and out.is_contiguous()) or x.dtype != out.dtype:
         raise ValueError("row_resample needs contiguous tensors of one dtype")
-    es = {torch.bfloat16: 2, torch.float32: 4}[x.dtype]
     check(load().avc_row_resample(
-        C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int32(es), C.c_int32(x.shape[0]),
+        C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int32(dtype_code(x.dtype)), C.c_int32(x.shape[0]),
         C.c_int32(x.shape[1]), C.c_int32(out.shape[1]), C.c_int32(x.shape[2]), C.c_void_p(row_ptr.data_ptr()),
         C.c_void_p(col_idx.data_ptr()), C.c_void_p(weight.data_ptr()), stream_ptr()))
 

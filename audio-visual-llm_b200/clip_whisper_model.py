@@ -10,6 +10,10 @@ New keyword arguments default to the reference's behaviour:
 `align="rate"` pairs 2 Whisper frames (50 Hz) with 1 CLIP frame (25 fps): k_a = stride, k_v = stride / 2; at
 stride 1 every video frame is used for two consecutive tokens instead (video_repeat = 2).
 
+`use_fp16=True` gives an fp16 LLM / fp16 `inputs_embeds` as in the reference (:164); `freeze_encoders=False` lets the
+connector's input gradients (dX GEMM + the gather's transpose) flow into the towers (:1096, :1136); `use_lora`,
+`use_4bit` and `freeze_llm` act on the LLM tower exactly as in the reference's `_load_llm` (:896-1016).
+
 There is no CPU fallback (the reference's `"cuda" if torch.cuda.is_available() else "cpu"` default,
 clip_whisper_model.py:91, is removed): the device must be an sm_100 GPU.
 """
@@ -66,9 +70,6 @@ class ClipWhisperModel(nn.Module):
             raise L.ConnectorError(f"device={device!r}: the B200 connector path has no CPU fallback")
         idx = torch.device(device).index
         L.require_device(0 if idx is None else idx)
-        if not freeze_encoders:
-            raise NotImplementedError("freeze_encoders=False needs input gradients (dX), which this path does not "
-                                      "produce; the reference default is True (configs/clip_whisper.yaml:28)")
         if align not in ("index", "rate"):
             raise ValueError("align must be 'index' or 'rate'")
         self.device = device
@@ -95,7 +96,10 @@ class ClipWhisperModel(nn.Module):
         self.audio_stride, self.video_stride = ka, kv
         self.video_repeat = 2 if (align == "rate" and stride == 1 and video_stride is None) else 1
         self.mask_mode, self.label_mode = mask_mode, label_mode
-        self.dtype = torch.bfloat16 if use_fp16 else torch.float32  # reference: fp16 if use_fp16 (:164)
+        self.dtype = torch.float16 if use_fp16 else torch.float32  # clip_whisper_model.py:164
+        self.use_4bit, self.use_lora = use_4bit, use_lora
+        self.lora_r, self.lora_alpha, self.lora_dropout = lora_r, lora_alpha, lora_dropout
+        self.grad_sync = None  # parallel.FusedGradSync once enable_data_parallel() has been called
 
         self.tokenizer = _provided_tokenizer
         self.llm = _provided_llm
@@ -103,14 +107,17 @@ class ClipWhisperModel(nn.Module):
         self.clip = _provided_clip
         if self.llm is None or self.tokenizer is None:
             self.tokenizer, self.llm = self._load_llm(llm_path)
+        elif freeze_llm:
+            self._freeze_llm(self.llm, keep_lora=use_lora)  # a provided LLM is frozen the same way (:1005-1014)
         if self.whisper is None and modality in ("audio", "both"):
             self.whisper = self._load_tower("WhisperModel", whisper_model)
         if self.clip is None and modality in ("video", "both"):
             self.clip = self._load_tower("CLIPVisionModel", clip_model)
-        for tower in (self.whisper, self.clip):
-            if tower is not None:
-                for p in tower.parameters():
-                    p.requires_grad = False  # clip_whisper_model.py:873, 893
+        if freeze_encoders:
+            for tower in (self.whisper, self.clip):
+                if tower is not None:
+                    for p in tower.parameters():
+                        p.requires_grad = False  # clip_whisper_model.py:873, 893
 
         # dims as the reference derives them (:216, :247, :1148-1157); defaults for an absent modality (:223, :254)
         self.audio_dim = audio_dim or (self.whisper.config.d_model if self.whisper is not None else 1024)
@@ -120,13 +127,53 @@ class ClipWhisperModel(nn.Module):
 
     # ------------------------------------------------------------------ construction helpers
     def _load_llm(self, llm_path):
+        """clip_whisper_model.py:896-1016: optional 4-bit load, optional LoRA wrap (scaled-down init), optional
+        freeze that leaves the LoRA weights trainable.  The LLM is a tower (untouched PyTorch / peft / bitsandbytes);
+        a flag whose library is missing raises instead of being ignored."""
         from transformers import AutoModelForCausalLM, AutoTokenizer
 
-        tok = AutoTokenizer.from_pretrained(llm_path)
+        tok = self.tokenizer if self.tokenizer is not None else AutoTokenizer.from_pretrained(llm_path)
         if tok.pad_token is None:
             tok.pad_token = tok.eos_token  # clip_whisper_model.py:955-959
-        llm = AutoModelForCausalLM.from_pretrained(llm_path, torch_dtype=self.dtype).to(self.device)
+        if self.use_4bit:
+            try:
+                import bitsandbytes  # noqa: F401
+                from transformers import BitsAndBytesConfig
+            except ImportError as e:
+                raise NotImplementedError("use_4bit=True needs bitsandbytes (clip_whisper_model.py:905-928), which is "
+                                          "not installed; pass use_4bit=False or a pre-quantised _provided_llm") from e
+            q = BitsAndBytesConfig(load_in_4bit=True, bnb_4bit_compute_dtype=self.dtype, bnb_4bit_use_double_quant=True,
+                                   bnb_4bit_quant_type="nf4")
+            llm = AutoModelForCausalLM.from_pretrained(llm_path, device_map="auto", quantization_config=q,
+                                                       torch_dtype=self.dtype)
+        else:
+            llm = AutoModelForCausalLM.from_pretrained(llm_path, torch_dtype=self.dtype).to(self.device)
+        if self.use_lora:
+            try:
+                from peft import LoraConfig, get_peft_model
+            except ImportError as e:
+                raise NotImplementedError("use_lora=True (the reference default) needs peft (clip_whisper_model.py:"
+                                          "962-1002), which is not installed; pass use_lora=False or a _provided_llm "
+                                          "that is already wrapped") from e
+            targets = ["q_proj", "k_proj", "v_proj", "o_proj"] if "llama" in llm_path.lower() else \
+                ["query", "key", "value", "dense"]
+            llm = get_peft_model(llm, LoraConfig(r=self.lora_r, lora_alpha=self.lora_alpha,
+                                                 lora_dropout=self.lora_dropout, bias="none", task_type="CAUSAL_LM",
+                                                 target_modules=targets, init_lora_weights="gaussian",
+                                                 fan_in_fan_out=False))
+            with torch.no_grad():  # the reference scales the fresh LoRA weights down by 100 (:984-995)
+                for n, prm in llm.named_parameters():
+                    if "lora_" in n and prm.requires_grad:
+                        prm.mul_(0.01)
+        if self.freeze_llm:
+            self._freeze_llm(llm, keep_lora=self.use_lora)
         return tok, llm
+
+    @staticmethod
+    def _freeze_llm(llm, keep_lora: bool):
+        """freeze_llm (clip_whisper_model.py:1005-1014): everything frozen except, with LoRA, the adapter weights."""
+        for n, prm in llm.named_parameters():
+            prm.requires_grad = bool(keep_lora and "lora" in n)
 
     def _load_tower(self, cls_name, path):
         import transformers
@@ -152,6 +199,29 @@ class ClipWhisperModel(nn.Module):
                         video_stride=self.video_stride, video_repeat=self.video_repeat, mask_mode=self.mask_mode,
                         label_mode=self.label_mode)
 
+    def train(self, mode: bool = True):
+        """Mode switches drop the forward-only bf16 weight-pack cache: an optimizer that updated the parameters through
+        raw pointers between two evaluations did not bump torch's version counter (connector_ops.pack_projector)."""
+        from .connector_ops import invalidate_pack_cache
+
+        invalidate_pack_cache()
+        return super().train(mode)
+
+    def enable_data_parallel(self, process_group=None, multimem=None):
+        """One process per GPU: route the projector gradients of `forward()`'s backward into a peer-mapped bucket that
+        the dW GEMM launch all-reduces itself (parallel.FusedGradSync; insertion point between loss.backward() and
+        clip_grad_norm_, clip_whisper_trainer.py:454-458).  The parameters' .grad become views of that bucket."""
+        from .parallel import FusedGradSync
+
+        if self.connector_type != "simple":
+            raise NotImplementedError("the fused gradient all-reduce covers the linear projector ('simple')")
+        use_a, use_v = self.modality in ("audio", "both"), self.modality in ("video", "both")
+        ac, vc = self.audio_connector.linear, self.video_connector.linear
+        self.grad_sync = FusedGradSync(ac.weight if use_a else None, ac.bias if use_a else None,
+                                       vc.weight if use_v else None, vc.bias if use_v else None,
+                                       process_group=process_group, multimem=multimem)
+        return self.grad_sync
+
     # ------------------------------------------------------------------ towers (untouched PyTorch)
     def _whisper_features(self, audio, attention_mask=None):
         """Input checks and tower call of encode_audio (clip_whisper_model.py:1067-1103)."""
@@ -165,7 +235,7 @@ class ClipWhisperModel(nn.Module):
         whisper_dtype = next(self.whisper.parameters()).dtype
         if audio.dtype != whisper_dtype:
             audio = audio.to(whisper_dtype)
-        with torch.no_grad():
+        with torch.set_grad_enabled(not self.freeze_encoders and torch.is_grad_enabled()):  # :1096
             out = self.whisper.encoder(audio, attention_mask=attention_mask, output_hidden_states=True,
                                        return_dict=True)
         return out.last_hidden_state
@@ -181,7 +251,7 @@ class ClipWhisperModel(nn.Module):
         clip_dtype = next(self.clip.parameters()).dtype
         if flat.dtype != clip_dtype:
             flat = flat.to(clip_dtype)
-        with torch.no_grad():
+        with torch.set_grad_enabled(not self.freeze_encoders and torch.is_grad_enabled()):  # :1136
             hidden = self.clip(flat, return_dict=True).last_hidden_state  # [B*F, 1+Np, Dv]
         if not hidden.is_contiguous():
             hidden = hidden.contiguous()
@@ -221,7 +291,7 @@ class ClipWhisperModel(nn.Module):
         return None if ids is None else self.llm.get_input_embeddings()(ids)
 
     def _fused(self, audio, video, prompt=None, labels=None, input_ids=None, placeholder_id=-1,
-               audio_lengths=None, video_lengths=None):
+               audio_lengths=None, video_lengths=None, total_tokens=None):
         a = v = None
         if self.modality in ("audio", "both") and audio is not None:
             a = self._whisper_features(audio)
@@ -232,39 +302,63 @@ class ClipWhisperModel(nn.Module):
         llm_dtype = next(self.llm.parameters()).dtype  # clip_whisper_model.py:454
         table = self.llm.get_input_embeddings().weight
         pad_id = self.tokenizer.pad_token_id if self.tokenizer is not None else 0
+        prompt_ids = self._prompt_ids(prompt)
+        if self.connector_type == "adaptive":
+            raise NotImplementedError("the 'adaptive' connector is a stand-alone module (encode_audio / encode_video); "
+                                      "the fused encode() / forward() path needs connector_type 'simple' or 'mlp'")
         if self.connector_type == "mlp":
-            return fused_connector(
+            out = fused_connector(
                 a, v, None, None, None, None, self._plan(), input_ids=input_ids,
-                prompt_ids=self._prompt_ids(prompt), placeholder_id=placeholder_id, embed_table=table.detach(),
+                prompt_ids=prompt_ids, placeholder_id=placeholder_id, embed_table=table.detach(),
                 labels=labels, pad_id=pad_id, out_dtype=llm_dtype, audio_lengths=audio_lengths,
-                video_lengths=video_lengths, mlp_audio=self.audio_connector.mlp_params(),
+                video_lengths=video_lengths, total_tokens=total_tokens, mlp_audio=self.audio_connector.mlp_params(),
                 mlp_video=self.video_connector.mlp_params())
-        return fused_connector(
-            a, v, self.audio_connector.linear.weight, self.audio_connector.linear.bias,
-            self.video_connector.linear.weight, self.video_connector.linear.bias, self._plan(),
-            input_ids=input_ids, prompt_ids=self._prompt_ids(prompt), placeholder_id=placeholder_id,
-            embed_table=table.detach(), labels=labels, pad_id=pad_id, out_dtype=llm_dtype,
-            audio_lengths=audio_lengths, video_lengths=video_lengths)
+        else:
+            out = fused_connector(
+                a, v, self.audio_connector.linear.weight, self.audio_connector.linear.bias,
+                self.video_connector.linear.weight, self.video_connector.linear.bias, self._plan(),
+                input_ids=input_ids, prompt_ids=prompt_ids, placeholder_id=placeholder_id,
+                embed_table=table.detach(), labels=labels, pad_id=pad_id, out_dtype=llm_dtype,
+                audio_lengths=audio_lengths, video_lengths=video_lengths, total_tokens=total_tokens,
+                grad_sync=self.grad_sync if (self.training and torch.is_grad_enabled()) else None)
+        if table.requires_grad and torch.is_grad_enabled():
+            out = (self._differentiable_text_rows(out[0], table, input_ids, prompt_ids, placeholder_id),) + out[1:]
+        return out
+
+    def _differentiable_text_rows(self, emb, table, input_ids, prompt_ids, placeholder_id):
+        """The splice kernel copies text rows from a detached table.  When the LLM's input embeddings are trainable
+        (no LoRA / no freeze) the reference's `embedding_layer(prompt_ids)` (clip_whisper_model.py:484-485) is
+        differentiable, so the text rows are re-written from the live embedding layer (same values, with a graph)."""
+        layer = self.llm.get_input_embeddings()
+        if input_ids is None:
+            if prompt_ids is None:
+                return emb
+            P = prompt_ids.shape[1]
+            return torch.cat([layer(prompt_ids).to(emb.dtype), emb[:, P:]], dim=1)
+        ids = input_ids.to(emb.device)
+        text = (ids != placeholder_id) & (ids >= 0) & (ids < table.shape[0])
+        rows = layer(ids.clamp(0, table.shape[0] - 1)).to(emb.dtype)
+        return torch.where(text.unsqueeze(-1), rows, emb)
 
     def encode(self, audio=None, video=None, prompt=None, input_ids=None, placeholder_id=-1,
-               audio_lengths=None, video_lengths=None):
+               audio_lengths=None, video_lengths=None, total_tokens=None):
         """(inputs_embeds [B, P+T, H] in the LLM dtype, attention_mask int64 [B, P+T]) -- clip_whisper_model.py:407-462.
 
         Extension: `input_ids` containing `placeholder_id` runs selects the splice positions instead of the
         reference's fixed `[prompt | AV]` layout."""
         emb, mask, _ = self._fused(audio, video, prompt, None, input_ids, placeholder_id, audio_lengths,
-                                   video_lengths)
+                                   video_lengths, total_tokens)
         return emb, mask
 
     def forward(self, audio=None, video=None, prompt=None, labels=None, return_loss=True, input_ids=None,
-                placeholder_id=-1, audio_lengths=None, video_lengths=None):
+                placeholder_id=-1, audio_lengths=None, video_lengths=None, total_tokens=None):
         """clip_whisper_model.py:489-619."""
         use_labels = labels is not None and return_loss
         if use_labels:
             labels = self._coerce_labels(labels)
         # eval rule (pad -> -100, truncate / right-pad) is produced by the splice kernel
         emb, mask, lab = self._fused(audio, video, prompt, labels if use_labels else None, input_ids,
-                                     placeholder_id, audio_lengths, video_lengths)
+                                     placeholder_id, audio_lengths, video_lengths, total_tokens)
         if use_labels and self.training and labels.shape[1] != emb.shape[1]:
             # training branch (:577-585): sequence is resampled to the label length, labels only get pad -> -100
             emb = adaptive_projection(emb, labels.shape[1])

@@ -15,6 +15,7 @@ W = [sa*Wa | sv*Wv] and bias sa*ba*1[audio token] + sv*bv*1[video token] (SURVEY
 """
 from __future__ import annotations
 
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
@@ -24,7 +25,14 @@ import torch
 from . import _lib as L
 
 MAX_PROMPT_LEN = 32  # clip_whisper_model.py:469
-_SUPPORTED_OUT = (torch.float32, torch.bfloat16)
+# bf16 (training configuration), fp16 (the reference's use_fp16 mode, clip_whisper_model.py:164), fp32 (its default)
+_SUPPORTED_OUT = (torch.float32, torch.bfloat16, torch.float16)
+
+
+def _bias_in_gemm() -> bool:
+    """db comes out of the dW GEMM launch (extra work items of its tile schedule) unless AVC_BIAS_IN_GEMM=0 selects
+    the stand-alone column-sum kernel."""
+    return os.environ.get("AVC_BIAS_IN_GEMM", "1") != "0"
 
 
 @dataclass(frozen=True)
@@ -78,23 +86,34 @@ def to_bf16_features(x: torch.Tensor) -> torch.Tensor:
         raise ValueError(f"features must be [batch, frames, dim], got {tuple(x.shape)}")
     if x.dtype == torch.bfloat16 and x.stride(2) == 1:
         return x
-    if x.dtype != torch.float32 or x.stride(2) != 1:
+    if x.dtype not in L.DTYPE_CODES or x.stride(2) != 1 or (x.stride(1) * x.element_size()) % 16 or \
+            x.data_ptr() % 16:
         x = x.float().contiguous()
     B, T, D = x.shape
+    if D % 8:
+        raise ValueError(f"feature dim {D} must be a multiple of 8 (128-bit bf16 vectors)")
     out = torch.empty(B, T, D, dtype=torch.bfloat16, device=x.device)
     if B * T == 0:
         return out
     if x.stride(0) == T * x.stride(1):  # uniform row pitch (dense, or a CLS view of [B*F, 1+Np, D])
         src2d = torch.as_strided(x, (B * T, D), (x.stride(1), 1))
-        L.pack_weight(src2d, out.view(B * T, D), 1.0)
+        L.cast_bf16(src2d, out.view(B * T, D))
     else:
         for b in range(B):
-            L.pack_weight(x[b], out[b], 1.0)
+            L.cast_bf16(x[b], out[b])
     return out
 
 
 _PACK_CACHE: dict = {}
 _PACK_CACHE_MAX = 16
+
+
+def invalidate_pack_cache() -> None:
+    """Drop every cached bf16 weight pack.  The cache is validated by tensor identity + torch's version counter, which
+    an update through raw pointers (`ConnectorAdamW.step`, apex / DeepSpeed flat-parameter optimizers, any write via
+    `.data` from a custom kernel) does not bump: such optimizers must call this after they change the weights.
+    `ConnectorAdamW.step` and `ClipWhisperModel.train()/eval()` do."""
+    _PACK_CACHE.clear()
 
 
 def pack_projector(weights: Sequence[torch.Tensor], scales: Sequence[float], cache: bool = False) -> torch.Tensor:
@@ -139,15 +158,25 @@ def _as_int32(x, device) -> Optional[torch.Tensor]:
     return torch.tensor(list(x), dtype=torch.int32, device=device)
 
 
+def _to_bf16_rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D [rows, cols] bf16 / fp16 / fp32 -> bf16 (the dW GEMM's operand type); no copy if it already is."""
+    if t.dtype == torch.bfloat16:
+        return t
+    out = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    if t.numel():
+        L.cast_bf16(t, out)
+    return out
+
+
+def _grad_like(g: torch.Tensor, ref_dtype: torch.dtype) -> torch.Tensor:
+    return g if g.dtype == ref_dtype else g.to(ref_dtype)
+
+
 class _LinearProjectFn(torch.autograd.Function):
     """y = x . W^T + b on the tcgen05 projector GEMM (one modality; SimpleModalityConnector._forward_impl)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, out_dtype, cache_pack):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError(
-                "gradient w.r.t. connector inputs (unfrozen towers) is not produced by the B200 path; "
-                "the reference trains with freeze_encoders=True (configs/clip_whisper.yaml:28)")
         xb = to_bf16_features(x if x.dim() == 3 else x.unsqueeze(0))
         B, T, D = xb.shape
         H = weight.shape[0]
@@ -155,44 +184,63 @@ class _LinearProjectFn(torch.autograd.Function):
         y = torch.empty(B, T, H, dtype=out_dtype, device=x.device)
         if B * T:
             L.proj_fwd([xb], [wp], y, bias0=bias)
-        ctx.save_for_backward(xb)
+        ctx.save_for_backward(xb, weight)
         ctx.shape = (H, D)
         ctx.squeeze = x.dim() == 2
+        ctx.x_dtype = x.dtype
         return y[0] if ctx.squeeze else y
 
     @staticmethod
     def backward(ctx, dy):
-        (xb,) = ctx.saved_tensors
+        xb, weight = ctx.saved_tensors
         H, D = ctx.shape
+        B, T = xb.shape[0], xb.shape[1]
         if ctx.squeeze:
             dy = dy.unsqueeze(0)
-        dyb = to_bf16_features(dy)
-        dw = torch.empty(H, D, dtype=torch.float32, device=dy.device)
-        db = torch.empty(H, dtype=torch.float32, device=dy.device)
-        if xb.shape[0] * xb.shape[1]:
-            L.proj_bwd_dw(dyb, [xb], [dw], [1.0])
-            L.colsum(dyb, db, None, L.colsum_workspace(H, dy.device))
-        else:
-            dw.zero_()
-            db.zero_()
-        return None, dw, db, None, None
+        dev = dy.device
+        dy2 = dy.reshape(B * T, H)
+        if dy2.stride(1) != 1 or dy2.stride(0) != H:
+            dy2 = dy2.contiguous()
+        dyb = _to_bf16_rows(dy2).view(B, T, H)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw = torch.empty(H, D, dtype=torch.float32, device=dev)
+            db = torch.empty(H, dtype=torch.float32, device=dev)
+            if B * T == 0:
+                dw.zero_()
+                db.zero_()
+            elif _bias_in_gemm():
+                L.proj_bwd_dw(dyb, [xb], [dw], [1.0], bias=(L.present_operand(B, T, dev), db, None, 1.0, 1.0))
+            else:
+                L.proj_bwd_dw(dyb, [xb], [dw], [1.0])
+                L.colsum(dyb, db, None, L.colsum_workspace(H, dev))
+        if ctx.needs_input_grad[0]:
+            # unfrozen tower (freeze_encoders=False, clip_whisper_model.py:1096,1136): dX = dY . W on the same TN GEMM
+            gdt = ctx.x_dtype if ctx.x_dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
+            dx = torch.empty(B, T, D, dtype=gdt, device=dev)
+            if B * T:
+                wt = torch.empty(D, H, dtype=torch.bfloat16, device=dev)
+                L.pack_weight_t(weight, wt, 1.0)
+                L.proj_bwd_dx([dyb], [wt], dx)
+            dx = _grad_like(dx[0] if ctx.squeeze else dx, ctx.x_dtype)
+        return dx, dw, db, None, None
 
 
 def linear_project(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     if out_dtype not in _SUPPORTED_OUT:
-        raise L.ConnectorError(f"connector output dtype {out_dtype} unsupported on the B200 path (fp32 or bf16)")
+        raise L.ConnectorError(f"connector output dtype {out_dtype} unsupported on the B200 path (fp32, bf16 or fp16)")
     _require_cuda(x, "connector input")
     recording = torch.is_grad_enabled() and (weight.requires_grad or bias.requires_grad)
     return _LinearProjectFn.apply(x, weight, bias, out_dtype, not recording)
 
 
 class _FusedConnectorFn(torch.autograd.Function):
-    """gather -> projector GEMM -> splice (+ masks); backward: splice-bwd -> dW GEMM + bias column sums."""
+    """gather -> projector GEMM -> splice (+ masks); backward: splice-bwd -> dW GEMM (+ db work items) [-> dX]."""
 
     @staticmethod
-    def forward(ctx, wa, ba, wv, bv, st):
+    def forward(ctx, wa, ba, wv, bv, audio_in, video_in, st):
         dev = st["device"]
-        audio, video = st["audio"], st["video"]
+        audio, video = st["audio"], st["video"]  # bf16 copies / views of audio_in, video_in
         plan: FusePlan = st["plan"]
         use_a, use_v = audio is not None, video is not None
         sa, sv = plan.scales(use_a, use_v)
@@ -252,15 +300,22 @@ class _FusedConnectorFn(torch.autograd.Function):
         sp = L.make_splice(ids, st["placeholder_id"], st["pad_id"], H, tokens_per_sample=N,
                            tok_offset=st["tok_offset"], embed_table=st["embed_table"], attention_mask=mask,
                            mask_mode=plan.mask_mode, label_mode=plan.label_mode, labels_in=st["labels"],
-                           labels_out=labels_out, status=status, elem_size=4 if out_dtype == torch.float32 else 2,
+                           labels_out=labels_out, status=status, elem_size=emb.element_size(),
                            av_rows_in_place=in_place)
         L.splice_fwd(sp, None if (in_place or not M) else Y, emb)
-        ctx.save_for_backward(*xs)
+        ctx.save_for_backward(*xs, *ws)
+        ctx.nx = len(xs)
         ctx.flags = flags
         ctx.sp = sp
         ctx.meta = (use_a, use_v, sa, sv, Ka, Kv, H, M, out_dtype)
         # uniform `[prompt | AV]` layout built by fused_connector itself: backward may read d(inputs_embeds) in place
         ctx.uniform = (B, N, S - N) if (st["uniform_layout"] and out_dtype == torch.bfloat16) else None
+        ctx.grad_sync = st.get("grad_sync")
+        # what the input gradients (unfrozen towers) need: the gather geometry and the raw inputs' layout
+        ctx.dx = dict(direct=direct, B=B, N=N, plan=plan, tok_offset=st["tok_offset"],
+                      audio_valid=st["audio_valid"], video_valid=st["video_valid"],
+                      a_meta=None if audio_in is None else (tuple(audio_in.shape), audio_in.dtype),
+                      v_meta=None if video_in is None else (tuple(video_in.shape), video_in.dtype))
         st["status"] = status
         st["row_flags"] = flags
         st["direct"] = direct
@@ -272,45 +327,105 @@ class _FusedConnectorFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_emb, *unused):
-        xs = list(ctx.saved_tensors)
+        saved = list(ctx.saved_tensors)
+        xs, ws = saved[:ctx.nx], saved[ctx.nx:]
         flags = ctx.flags
         use_a, use_v, sa, sv, Ka, Kv, H, M, out_dtype = ctx.meta
         dev = d_emb.device
+        want_w = any(ctx.needs_input_grad[:4])
+        want_x = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
         if d_emb.dtype != out_dtype or not d_emb.is_contiguous():
             d_emb = d_emb.to(out_dtype).contiguous()
-        dwa = torch.empty(H, Ka, dtype=torch.float32, device=dev) if use_a else None
-        dwv = torch.empty(H, Kv, dtype=torch.float32, device=dev) if use_v else None
-        dba = torch.empty(H, dtype=torch.float32, device=dev) if use_a else None
-        dbv = torch.empty(H, dtype=torch.float32, device=dev) if use_v else None
+        sync = ctx.grad_sync if want_w else None
+        if sync is not None:
+            dwa, dba, dwv, dbv = sync.views(use_a, use_v)
+        else:
+            dwa = torch.empty(H, Ka, dtype=torch.float32, device=dev) if (use_a and want_w) else None
+            dwv = torch.empty(H, Kv, dtype=torch.float32, device=dev) if (use_v and want_w) else None
+            dba = torch.empty(H, dtype=torch.float32, device=dev) if (use_a and want_w) else None
+            dbv = torch.empty(H, dtype=torch.float32, device=dev) if (use_v and want_w) else None
         if M == 0:
+            if sync is not None:
+                raise L.ConnectorError("data-parallel gradient sync needs at least one fused token on every rank")
             for t in (dwa, dwv, dba, dbv):
                 if t is not None:
                     t.zero_()
-            return dwa, dba, dwv, dbv, None
-        dws = ([dwa] if use_a else []) + ([dwv] if use_v else [])
-        al = ([sa] if use_a else []) + ([sv] if use_v else [])
-        ws = L.colsum_workspace(H, dev)
+            return dwa, dba, dwv, dbv, None, None, None
+        # ---- dY: d(inputs_embeds) read in place (`[prompt | AV]`, bf16) or gathered back into packed rows
         if ctx.uniform is not None:
-            # `[prompt | AV]`: the AV rows of sample b are rows P .. P+N-1 of d(inputs_embeds)[b]; the dW GEMM and
-            # the bias sums read them in place (no splice-bwd copy)
             B, N, P = ctx.uniform
+            dy, base = d_emb, P
             x3 = [x.view(B, N, x.shape[1]) for x in xs]
-            L.proj_bwd_dw(d_emb, x3, dws, al, dy_row_base=P)
-            if flags is None:
-                L.colsum(d_emb, dba, dbv, ws, alpha0=sa, alpha1=sv, dy_row_base=P, sum_rows=N)
+            present_shape = (B, N)
+        else:
+            dY = torch.empty(M, H, dtype=out_dtype, device=dev)
+            L.splice_bwd(ctx.sp, d_emb, dY)
+            dy, base = _to_bf16_rows(dY), 0
+            x3 = xs
+            present_shape = (1, M)
+        inv = 1.0 / sync.world if sync is not None else 1.0
+        if want_w:
+            dws = ([dwa] if use_a else []) + ([dwv] if use_v else [])
+            al = ([sa * inv] if use_a else []) + ([sv * inv] if use_v else [])
+            if _bias_in_gemm() or sync is not None:
+                bias = (L.present_operand(*present_shape, dev, row_flags=flags), dba, dbv, sa * inv, sv * inv)
+                if sync is not None:
+                    L.proj_bwd_dw_allreduce(dy, x3, dws, al, sync.next_epoch(), dy_row_base=base, bias=bias)
+                else:
+                    L.proj_bwd_dw(dy, x3, dws, al, dy_row_base=base, bias=bias)
             else:
-                L.colsum(d_emb, dba, dbv, ws, row_flags=flags, alpha0=sa, alpha1=sv, dy_row_base=P, sum_rows=N)
-            return dwa, dba, dwv, dbv, None
-        dY = torch.empty(M, H, dtype=out_dtype, device=dev)
-        L.splice_bwd(ctx.sp, d_emb, dY)
-        if out_dtype == torch.float32:
-            dYb = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
-            L.pack_weight(dY, dYb, 1.0)
-            dY = dYb
-        L.proj_bwd_dw(dY, xs, dws, al)
-        # flag bit0 = audio token present, bit1 = video token present (all present when the stack was a free view)
-        L.colsum(dY, dba, dbv, ws, row_flags=flags, alpha0=sa, alpha1=sv)
-        return dwa, dba, dwv, dbv, None
+                L.proj_bwd_dw(dy, x3, dws, al, dy_row_base=base)
+                # flag bit0 = audio token present, bit1 = video token present (all present when flags is None)
+                cs = dict(dy_row_base=base, sum_rows=present_shape[1]) if ctx.uniform is not None else {}
+                L.colsum(dy, dba, dbv, L.colsum_workspace(H, dev), row_flags=flags, alpha0=sa, alpha1=sv, **cs)
+        d_audio = d_video = None
+        if want_x:
+            d_audio, d_video = _input_grads(ctx, dy, base, ws, dev)
+        if sync is not None:
+            return None, None, None, None, d_audio, d_video, None  # the gradients live in the attached bucket views
+        return dwa, dba, dwv, dbv, d_audio, d_video, None
+
+
+def _input_grads(ctx, dy, base, ws, dev):
+    """d(audio), d(video) for unfrozen towers: dA_s = dY . (scale_s W_s) per modality on the TN GEMM, then the
+    transpose of the gather (a free reshape when the stack was one)."""
+    use_a, use_v, sa, sv, Ka, Kv, H, M, _ = ctx.meta
+    g = ctx.dx
+    plan: FusePlan = g["plan"]
+    B, N = g["B"], g["N"]
+    if ctx.uniform is not None:
+        dy_op = dy[:, base:, :]                     # [B, N, H] view of d(inputs_embeds)
+    else:
+        dy_op = dy                                  # packed [M, H]
+    outs = []
+    wi = 0
+    for use, need, meta, scale, k, rep, valid, col in (
+            (use_a, ctx.needs_input_grad[4], g["a_meta"], sa, plan.audio_stride, plan.audio_repeat, g["audio_valid"], 0),
+            (use_v, ctx.needs_input_grad[5], g["v_meta"], sv, plan.video_stride, plan.video_repeat, g["video_valid"], Ka)):
+        if not use:
+            outs.append(None)
+            continue
+        w = ws[wi]
+        wi += 1
+        if not need:
+            outs.append(None)
+            continue
+        (Bx, T, D), in_dtype = meta
+        Ks = w.shape[1]
+        wt = torch.empty(Ks, H, dtype=torch.bfloat16, device=dev)
+        L.pack_weight_t(w, wt, scale)
+        gdt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
+        if g["direct"]:
+            dx = torch.empty(B, N, Ks, dtype=gdt, device=dev)
+            L.proj_bwd_dx([dy_op], [wt], dx if ctx.uniform is not None else dx.view(B * N, Ks))
+            dx = dx.view(Bx, T, D)
+        else:
+            dA = torch.empty(M, Ks, dtype=torch.bfloat16, device=dev)
+            L.proj_bwd_dx([dy_op], [wt], dA if dy_op.dim() == 2 else dA.view(B, N, Ks))
+            dx = torch.empty(Bx, T, D, dtype=gdt, device=dev)
+            L.gather_bwd(dA, 0, dx, k, rep, B, N, tok_offset=g["tok_offset"], valid=valid)
+        outs.append(_grad_like(dx, in_dtype))
+    return outs[0], outs[1]
 
 
 def _stack_is_free_view(x: Optional[torch.Tensor], k: int, ntok: int) -> bool:
@@ -322,23 +437,71 @@ def _stack_is_free_view(x: Optional[torch.Tensor], k: int, ntok: int) -> bool:
             and x.data_ptr() % 16 == 0)
 
 
+def ragged_token_offsets(plan: FusePlan, batch: int, Ta: Optional[int], Tv: Optional[int], audio_lengths,
+                         video_lengths, device, total_tokens: Optional[int] = None):
+    """Per-sample fused-token counts -> exclusive prefix offsets [B+1] int32 on the device (+ clamped valid lengths).
+
+    Host lists / CPU tensors: the arithmetic runs on the host and one small H2D copy carries the offsets.  Device
+    tensors: the counts and their prefix sum are formed on the device (integer index bookkeeping, no feature data);
+    the only host synchronisation left is reading the total row count, which `total_tokens` (e.g. the number of
+    placeholders the data pipeline put into input_ids) removes.  Returns (tok_offset, audio_valid, video_valid, rows).
+    """
+    def on_device(x):
+        return isinstance(x, torch.Tensor) and x.is_cuda
+
+    if on_device(audio_lengths) or on_device(video_lengths):
+        cnt = None
+        av = vv = None
+        if Ta is not None and audio_lengths is not None:
+            av = torch.as_tensor(audio_lengths, device=device).to(torch.int32).clamp(0, Ta)
+        if Tv is not None and video_lengths is not None:
+            vv = torch.as_tensor(video_lengths, device=device).to(torch.int32).clamp(0, Tv)
+        for T, valid, k, rep in ((Ta, av, plan.audio_stride, plan.audio_repeat),
+                                 (Tv, vv, plan.video_stride, plan.video_repeat)):
+            if T is None:
+                continue
+            ln = valid if valid is not None else torch.full((batch,), T, dtype=torch.int32, device=device)
+            n = torch.div(ln + (k - 1), k, rounding_mode="floor") * rep
+            cnt = n if cnt is None else torch.maximum(cnt, n)
+        if Ta is not None and Tv is not None:
+            cnt = cnt.clamp(max=plan.max_seq_len)
+        offs = torch.zeros(batch + 1, dtype=torch.int32, device=device)
+        offs[1:] = torch.cumsum(cnt, 0)
+        rows = int(total_tokens) if total_tokens is not None else int(offs[-1].item())
+        return offs, av, vv, rows
+    la = None if Ta is None or audio_lengths is None else [min(max(int(x), 0), Ta) for x in _host_list(audio_lengths)]
+    lv = None if Tv is None or video_lengths is None else [min(max(int(x), 0), Tv) for x in _host_list(video_lengths)]
+    offs = [0]
+    for b in range(batch):
+        offs.append(offs[-1] + plan.tokens(la[b] if la is not None else Ta, lv[b] if lv is not None else Tv))
+    if total_tokens is not None and int(total_tokens) != offs[-1]:
+        raise ValueError(f"total_tokens={total_tokens} but the lengths give {offs[-1]} fused tokens")
+    return (torch.tensor(offs, dtype=torch.int32, device=device), _as_int32(la, device), _as_int32(lv, device),
+            offs[-1])
+
+
 def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor], wa, ba, wv, bv, plan: FusePlan, *,
                     input_ids: Optional[torch.Tensor] = None, prompt_ids: Optional[torch.Tensor] = None,
                     placeholder_id: int = -1, embed_table: Optional[torch.Tensor] = None,
                     labels: Optional[torch.Tensor] = None, pad_id: int = 0, out_dtype: torch.dtype = torch.bfloat16,
-                    audio_lengths=None, video_lengths=None, check: bool = False, mlp_audio=None, mlp_video=None):
+                    audio_lengths=None, video_lengths=None, total_tokens: Optional[int] = None, check: bool = False,
+                    mlp_audio=None, mlp_video=None, grad_sync=None):
     """Tower features -> (inputs_embeds [B, S, H], attention_mask int64 [B, S], labels int64 [B, S] | None).
 
-    audio [B, Ta, Da] / video [B, Tv, Dv] (video may be a strided CLS view of CLIP's last_hidden_state).
+    audio [B, Ta, Da] / video [B, Tv, Dv] (video may be a strided CLS view of CLIP's last_hidden_state); features that
+    require grad (unfrozen towers, freeze_encoders=False) receive input gradients from the backward.
     mlp_audio / mlp_video = (fc1.weight, fc1.bias, fc2.weight, fc2.bias) select the two-layer GELU projector
     instead of the linear one (wa, ba, wv, bv are then ignored).
     Layout: `input_ids` with `placeholder_id` runs marks where the AV tokens go; without it the reference layout
     `[prompt_ids[:, :32] | AV tokens]` is built (clip_whisper_model.py:448-451).
     audio_lengths / video_lengths (host ints or int32 tensors, valid frames per sample) switch to ragged packing:
-    sample b contributes ntok_b = tokens(len_a[b], len_v[b]) rows and needs exactly ntok_b placeholders.
+    sample b contributes ntok_b = tokens(len_a[b], len_v[b]) rows and needs exactly ntok_b placeholders
+    (`total_tokens` = their sum, if the caller knows it, saves the host read of the device-side prefix sum).
+    grad_sync (`parallel.FusedGradSync`): data parallel -- the backward writes dW / db into the peer-mapped bucket the
+    parameters' .grad point at and all-reduces them inside the dW GEMM launch (no NCCL call, no .grad returned).
     """
     if out_dtype not in _SUPPORTED_OUT:
-        raise L.ConnectorError(f"LLM dtype {out_dtype} unsupported on the B200 path (fp32 or bf16)")
+        raise L.ConnectorError(f"LLM dtype {out_dtype} unsupported on the B200 path (fp32, bf16 or fp16)")
     use_a = plan.modality in ("audio", "both") and audio is not None
     use_v = plan.modality in ("video", "both") and video is not None
     if not (use_a or use_v):
@@ -354,19 +517,9 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
     rows = B * N
     ragged = audio_lengths is not None or video_lengths is not None
     if ragged:
-        la = None if not use_a or audio_lengths is None else [min(int(x), a.shape[1]) for x in _host_list(audio_lengths)]
-        lv = None if not use_v or video_lengths is None else [min(int(x), v.shape[1]) for x in _host_list(video_lengths)]
-        counts = []
-        for b in range(B):
-            counts.append(plan.tokens(la[b] if la is not None else (a.shape[1] if use_a else None),
-                                      lv[b] if lv is not None else (v.shape[1] if use_v else None)))
-        offs = [0]
-        for c in counts:
-            offs.append(offs[-1] + c)
-        rows = offs[-1]
-        tok_offset = torch.tensor(offs, dtype=torch.int32, device=dev)
-        audio_valid = _as_int32(la, dev)
-        video_valid = _as_int32(lv, dev)
+        tok_offset, audio_valid, video_valid, rows = ragged_token_offsets(
+            plan, B, a.shape[1] if use_a else None, v.shape[1] if use_v else None, audio_lengths, video_lengths, dev,
+            total_tokens)
     uniform_layout = input_ids is None
     if input_ids is None:
         ph = torch.full((B, N), placeholder_id, dtype=torch.int64, device=dev)
@@ -389,20 +542,26 @@ def fused_connector(audio: Optional[torch.Tensor], video: Optional[torch.Tensor]
     st = dict(device=dev, audio=a, video=v, plan=plan, batch=B, ntok=N, rows=rows, tok_offset=tok_offset,
               audio_valid=audio_valid, video_valid=video_valid, out_dtype=out_dtype, input_ids=input_ids,
               placeholder_id=placeholder_id, pad_id=pad_id, embed_table=embed_table, labels=labels,
-              uniform_layout=uniform_layout)
+              uniform_layout=uniform_layout, grad_sync=grad_sync)
     trainable = [p for p in (wa, ba, wv, bv, *(mlp_audio or ()), *(mlp_video or ())) if isinstance(p, torch.Tensor)]
     st["cache_pack"] = not (torch.is_grad_enabled() and any(p.requires_grad for p in trainable))
     dummy = torch.zeros(0, device=dev)
+    x_grad = torch.is_grad_enabled() and ((use_a and audio.requires_grad) or (use_v and video.requires_grad))
     if mlp_audio is not None or mlp_video is not None:
         # Linear -> GELU -> Linear per modality: (fc1.weight, fc1.bias, fc2.weight, fc2.bias)
         from .mlp_ops import FusedMLPConnectorFn
 
+        if x_grad:
+            raise NotImplementedError("the MLP projector does not produce input gradients (unfrozen towers); use the "
+                                      "linear projector (connector_type='simple') with freeze_encoders=False")
+        if grad_sync is not None:
+            raise NotImplementedError("grad_sync covers the linear projector's gradient bucket only")
         pa = tuple(mlp_audio) if use_a else (dummy,) * 4
         pv = tuple(mlp_video) if use_v else (dummy,) * 4
         out = FusedMLPConnectorFn.apply(*pa, *pv, st)
     else:
         out = _FusedConnectorFn.apply(wa if use_a else dummy, ba if use_a else dummy, wv if use_v else dummy,
-                                      bv if use_v else dummy, st)
+                                      bv if use_v else dummy, audio if use_a else None, video if use_v else None, st)
     if check and int(st["status"].item()) != 0:
         raise L.ConnectorError("placeholder count does not match the number of fused tokens for some sample")
     emb, mask = out[0], out[1]

@@ -76,11 +76,13 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // 3-D tensor map over [batches][rows][cols] (cols contiguous), 128-byte swizzle.
-int make_map3d(CUtensorMap* map, const void* ptr, bool fp32, int64_t cols, int64_t rows,
+// elem: avc::GemmOut code of the element type (bf16 / fp32 / fp16)
+int make_map3d(CUtensorMap* map, const void* ptr, int elem, int64_t cols, int64_t rows,
                int64_t batches, int64_t row_stride_elems, int64_t batch_stride_elems, int box_cols,
                int box_rows, const char* what) {
   auto enc = encode_fn();
   if (enc == nullptr) return fail(AVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const bool fp32 = elem == avc::GEMM_OUT_F32;
   const int64_t es = fp32 ? 4 : 2;
   if (ptr == nullptr) return fail(AVC_ERR_INVALID, "%s: null pointer", what);
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(AVC_ERR_INVALID, "%s: base not 16-byte aligned", what);
@@ -97,7 +99,10 @@ int make_map3d(CUtensorMap* map, const void* ptr, bool fp32, int64_t cols, int64
                            static_cast<cuuint64_t>(batch_stride_elems * es)};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+  const CUtensorMapDataType dt = fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : (elem == avc::GEMM_OUT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                   : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(map, dt, 3,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -182,11 +187,14 @@ int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t batch, 
   return AVC_OK;
 }
 
-int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat* y, int32_t y_is_fp32,
+int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat* y, int32_t y_dtype,
                  const float* bias0, const float* bias1, float bias_scale0, float bias_scale1,
                  const uint8_t* row_flags, int32_t flag_rows0, int32_t flag_rows1, int32_t act, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
+  if (y_dtype != AVC_DTYPE_BF16 && y_dtype != AVC_DTYPE_F32 && y_dtype != AVC_DTYPE_F16)
+    return fail(AVC_ERR_INVALID, "proj_fwd: y_dtype must be AVC_DTYPE_BF16 (0), AVC_DTYPE_F32 (1) or AVC_DTYPE_F16 (2)");
+  const bool y_is_fp32 = y_dtype == AVC_DTYPE_F32;
   if (nseg < 1 || nseg > 2) return fail(AVC_ERR_INVALID, "proj_fwd: nseg must be 1 or 2");
   if (a == nullptr || w == nullptr || y == nullptr) return fail(AVC_ERR_INVALID, "proj_fwd: null matrix");
   if (act != 0 && act != 1) return fail(AVC_ERR_INVALID, "proj_fwd: act must be 0 or 1");
@@ -208,7 +216,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   g.m_tiles_per_batch = static_cast<int>(ceil_div(m_rows, avc::GEMM_BM * cg * mt));
   g.num_m_blocks = static_cast<int>(m_batches) * g.m_tiles_per_batch;
   if (scatter)
-    if (int rc = make_map3d(&g.md_row, y->ptr, y_is_fp32 != 0, N, y->rows, y->batches, y->row_stride,
+    if (int rc = make_map3d(&g.md_row, y->ptr, y_dtype, N, y->rows, y->batches, y->row_stride,
                             y->batch_stride, y_is_fp32 ? 32 : 64, 1, "proj_fwd Y (row box)"))
       return rc;
   g.scatter_rows = scatter ? static_cast<int>(y->rows) : 0;
@@ -231,7 +239,7 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
       return rc;
     g.seg_kblocks[s] = static_cast<int>(ceil_div(a[s].cols, avc::GEMM_BK));
   }
-  if (int rc = make_map3d(&g.md[0], y->ptr, y_is_fp32 != 0, N, y->rows, y->batches, y->row_stride,
+  if (int rc = make_map3d(&g.md[0], y->ptr, y_dtype, N, y->rows, y->batches, y->row_stride,
                           y->batch_stride, y_is_fp32 ? 32 : 64, 32, "proj_fwd Y"))
     return rc;
   g.num_n_blocks = static_cast<int>(ceil_div(N, g.bn));
@@ -249,10 +257,17 @@ int avc_proj_fwd(int32_t nseg, const avc_mat* a, const avc_mat* w, const avc_mat
   g.act = act;
   if ((bias0 && (reinterpret_cast<uintptr_t>(bias0) & 15)) || (bias1 && (reinterpret_cast<uintptr_t>(bias1) & 15)))
     return fail(AVC_ERR_INVALID, "proj_fwd: bias pointers must be 16-byte aligned");
-  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, y_is_fp32 != 0, cg, mt, di.num_sms,
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_TN, static_cast<avc::GemmOut>(y_dtype), cg, mt, di.num_sms,
                                    static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_fwd launch");
   return AVC_OK;
+}
+
+int avc_proj_bwd_dx(const avc_mat* dy, int32_t nseg, const avc_mat* w_t, const avc_mat* dx, int32_t dx_dtype,
+                    void* stream) {
+  // dX = dY . W is the forward GEMM with A = dY ([.., H], K-major in H) and B = W^T ([K_in, H], from avc_pack_weight_t)
+  if (dy == nullptr || w_t == nullptr || dx == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dx: null matrix");
+  return avc_proj_fwd(nseg, dy, w_t, dx, dx_dtype, nullptr, nullptr, 0.f, 0.f, nullptr, 0, 0, 0, stream);
 }
 
 // avc_comm -> kernel arguments (pointer / range validation; offsets are relative to the local bucket)
@@ -301,8 +316,8 @@ static int fill_comm(const avc_comm* c, const float* extra0, int64_t extra0_len,
 }
 
 static int proj_bwd_dw_impl(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
-                            const float* alpha, const avc::CommArgs* comm, uint64_t bucket_bytes, int32_t max_sms,
-                            void* stream) {
+                            const float* alpha, const avc_bias_grad* bias, const avc::CommArgs* comm,
+                            uint64_t bucket_bytes, int32_t max_sms, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (max_sms < 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: negative max_sms");
@@ -348,6 +363,26 @@ static int proj_bwd_dw_impl(const avc_mat* dy, int32_t dy_row_base, int32_t nseg
   g.red_kblocks_per_batch = static_cast<int>(ceil_div(red_rows, avc::GEMM_BK));
   g.a_row_base = dy_row_base;
   g.d_rows = static_cast<int>(H);
+  if (bias != nullptr) {
+    // db inside the same launch: one 64-wide work item per M block contracts the dY panel with the token-present
+    // operand F (bf16 [batches][rows][64]: column 0 / 1 = the row carries an audio / video token)
+    const avc_mat* f = bias->present;
+    if (f == nullptr || f->ptr == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_db: null token-present operand");
+    if (f->cols != avc::GEMM_BIAS_COLS)
+      return fail(AVC_ERR_INVALID, "proj_bwd_dw_db: token-present operand must have %d columns", avc::GEMM_BIAS_COLS);
+    if (f->batches != dy->batches || f->rows < red_rows)
+      return fail(AVC_ERR_INVALID, "proj_bwd_dw_db: token-present operand must be [batches][>= X rows][%d]",
+                  avc::GEMM_BIAS_COLS);
+    if (bias->out0 == nullptr && bias->out1 == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_db: no output");
+    if (int rc = make_map3d(&g.mf, f->ptr, 0, f->cols, red_rows, f->batches, f->row_stride, f->batch_stride, 64,
+                            avc::GEMM_BK, "proj_bwd_dw_db F"))
+      return rc;
+    g.bias_items = g.num_m_blocks;
+    g.bias_out[0] = bias->out0;
+    g.bias_out[1] = bias->out1;
+    g.bias_alpha[0] = bias->alpha0;
+    g.bias_alpha[1] = bias->alpha1;
+  }
   if (comm != nullptr) {
     if (cg != 2) return fail(AVC_ERR_UNSUPPORTED, "proj_bwd_dw_allreduce needs the CTA-pair GEMM (AVC_GEMM_CTA_GROUP=2)");
     g.comm = *comm;
@@ -365,14 +400,33 @@ static int proj_bwd_dw_impl(const avc_mat* dy, int32_t dy_row_base, int32_t nseg
       return fail(AVC_ERR_UNSUPPORTED, "proj_bwd_dw_allreduce: %d work items exceed the flag area (%d)", items,
                   avc::COMM_MAX_ITEMS);
   }
-  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, true, cg, mt, di.num_sms, static_cast<cudaStream_t>(stream));
+  cudaError_t e = avc::launch_gemm(g, avc::GEMM_NT, avc::GEMM_OUT_F32, cg, mt, di.num_sms,
+                                   static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "proj_bwd_dw launch");
   return AVC_OK;
 }
 
 int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
                     const float* alpha, int32_t max_sms, void* stream) {
-  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, nullptr, 0, max_sms, stream);
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, nullptr, nullptr, 0, max_sms, stream);
+}
+
+int avc_proj_bwd_dw_db(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
+                       const float* alpha, const avc_bias_grad* bias, int32_t max_sms, void* stream) {
+  if (bias == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_db: null bias descriptor");
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, bias, nullptr, 0, max_sms, stream);
+}
+
+int avc_proj_bwd_dw_db_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
+                                 const avc_mat* dw, const float* alpha, const avc_bias_grad* bias,
+                                 const avc_comm* comm, int32_t max_sms, void* stream) {
+  if (bias == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_db_allreduce: null bias descriptor");
+  if (dy == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_db_allreduce: null dY");
+  avc::CommArgs c;
+  // the bias gradients are the launch's extra ranges: produced by its own bias items, reduced by its comm warps
+  if (int rc = fill_comm(comm, bias->out0, bias->out0 ? dy->cols : 0, bias->out1, bias->out1 ? dy->cols : 0, &c))
+    return rc;
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, bias, &c, comm->bucket_bytes, max_sms, stream);
 }
 
 int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
@@ -381,7 +435,7 @@ int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t ns
                               void* stream) {
   avc::CommArgs c;
   if (int rc = fill_comm(comm, extra0, extra0_len, extra1, extra1_len, &c)) return rc;
-  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, &c, comm->bucket_bytes, max_sms, stream);
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, nullptr, &c, comm->bucket_bytes, max_sms, stream);
 }
 
 int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extra1_len, void* stream) {
@@ -529,6 +583,55 @@ int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t ds
   return AVC_OK;
 }
 
+int avc_cast_bf16(const void* src, int32_t src_dtype, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows,
+                  int64_t cols, float alpha, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (src == nullptr || dst_bf16 == nullptr) return fail(AVC_ERR_INVALID, "cast_bf16: null pointer");
+  if (src_dtype != AVC_DTYPE_BF16 && src_dtype != AVC_DTYPE_F32 && src_dtype != AVC_DTYPE_F16)
+    return fail(AVC_ERR_INVALID, "cast_bf16: src_dtype must be an AVC_DTYPE_* code");
+  cudaError_t e = avc::launch_cast_bf16(src, src_dtype, src_ld, dst_bf16, dst_ld, rows, cols, alpha,
+                                        static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "cast_bf16 launch");
+  return AVC_OK;
+}
+
+int avc_gather_bwd(const void* da, int64_t a_row_stride, int64_t col_off, const avc_feat* feat, int32_t out_dtype,
+                   int32_t batch, const int32_t* tok_offset, int32_t tokens_per_sample, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  if (da == nullptr || feat == nullptr || feat->ptr == nullptr) return fail(AVC_ERR_INVALID, "gather_bwd: null pointer");
+  if (out_dtype != AVC_DTYPE_BF16 && out_dtype != AVC_DTYPE_F32)
+    return fail(AVC_ERR_INVALID, "gather_bwd: out_dtype must be AVC_DTYPE_BF16 or AVC_DTYPE_F32");
+  if (batch <= 0) return fail(AVC_ERR_INVALID, "gather_bwd: batch must be positive");
+  if (feat->dim <= 0 || feat->dim % 8 != 0) return fail(AVC_ERR_INVALID, "gather_bwd: dim must be a positive multiple of 8");
+  if (feat->stack < 1 || feat->frames < 0 || feat->repeat < 0) return fail(AVC_ERR_INVALID, "gather_bwd: bad stack / frames / repeat");
+  if (tok_offset == nullptr && tokens_per_sample <= 0)
+    return fail(AVC_ERR_INVALID, "gather_bwd: tokens_per_sample must be positive when tok_offset is NULL");
+  if (col_off < 0 || a_row_stride < col_off + static_cast<int64_t>(feat->stack) * feat->dim)
+    return fail(AVC_ERR_INVALID, "gather_bwd: segment [col_off, col_off + stack * dim) exceeds the dA row");
+  const int es = out_dtype == AVC_DTYPE_F32 ? 4 : 2;
+  avc::GatherBwdArgs g;
+  memset(&g, 0, sizeof(g));
+  g.da = static_cast<const uint8_t*>(da);
+  g.a_row_stride = a_row_stride;
+  g.col_off = col_off;
+  g.dst = static_cast<uint8_t*>(const_cast<void*>(feat->ptr));
+  g.batch_stride = feat->batch_stride * es;
+  g.frame_stride = feat->frame_stride * es;
+  g.batch = batch;
+  g.frames = feat->frames;
+  g.dim = feat->dim;
+  g.k = feat->stack;
+  g.rep = feat->repeat > 0 ? feat->repeat : 1;
+  g.valid = feat->valid_frames;
+  g.tok_offset = tok_offset;
+  g.tokens_per_sample = tokens_per_sample;
+  cudaError_t e = avc::launch_gather_bwd(g, out_dtype == AVC_DTYPE_F32, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "gather_bwd launch");
+  return AVC_OK;
+}
+
 static int fill_splice(const avc_splice* s, avc::SpliceArgs* k) {
   if (s == nullptr || s->input_ids == nullptr) return fail(AVC_ERR_INVALID, "splice: null input_ids");
   if (s->hidden <= 0 || s->hidden % 8 != 0) return fail(AVC_ERR_INVALID, "splice: hidden must be a positive multiple of 8");
@@ -587,20 +690,21 @@ int avc_splice_bwd(const avc_splice* s, const void* d_inputs_embeds, void* dy, v
   return AVC_OK;
 }
 
-int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_t batch, int32_t src_rows, int32_t dst_rows,
+int avc_row_resample(const void* x, void* out, int32_t dtype, int32_t batch, int32_t src_rows, int32_t dst_rows,
                      int32_t hidden, const int32_t* row_ptr, const int32_t* col_idx, const float* weight,
                      void* stream) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (x == nullptr || out == nullptr || row_ptr == nullptr || col_idx == nullptr || weight == nullptr)
     return fail(AVC_ERR_INVALID, "row_resample: null pointer");
-  if (elem_size != 2 && elem_size != 4) return fail(AVC_ERR_INVALID, "row_resample: elem_size must be 2 or 4");
+  if (dtype != AVC_DTYPE_BF16 && dtype != AVC_DTYPE_F32 && dtype != AVC_DTYPE_F16)
+    return fail(AVC_ERR_INVALID, "row_resample: dtype must be an AVC_DTYPE_* code");
   if (batch < 0 || src_rows <= 0 || dst_rows < 0 || hidden <= 0) return fail(AVC_ERR_INVALID, "row_resample: bad extents");
   avc::ResampleArgs r;
   memset(&r, 0, sizeof(r));
   r.x = static_cast<const uint8_t*>(x);
   r.out = static_cast<uint8_t*>(out);
-  r.elem_size = elem_size;
+  r.dtype = dtype;
   r.batch = batch;
   r.src_rows = src_rows;
   r.dst_rows = dst_rows;

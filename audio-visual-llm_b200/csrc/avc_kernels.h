@@ -12,9 +12,16 @@ constexpr int GEMM_BN = 256;  // UMMA N (TMEM columns per accumulator stage)
 constexpr int GEMM_BK = 64;   // contraction elements per smem stage (= one 128-byte swizzle row)
 
 enum GemmMode : int {
-  GEMM_TN = 0,  // D[m,n] = sum_k A[m,k] * B[n,k]      (both operands K-major)   -> forward, dX-free
+  GEMM_TN = 0,  // D[m,n] = sum_k A[m,k] * B[n,k]      (both operands K-major)   -> forward, dX = dY . W
   GEMM_NT = 1,  // D[m,n] = sum_r A[r,m] * B[r,n]      (both operands MN-major)  -> dW = dY^T * X
 };
+// element type the epilogue writes (the accumulator is always fp32)
+enum GemmOut : int {
+  GEMM_OUT_BF16 = 0,
+  GEMM_OUT_F32 = 1,
+  GEMM_OUT_F16 = 2,  // the reference's use_fp16 mode (clip_whisper_model.py:164)
+};
+constexpr int GEMM_BIAS_COLS = 64;  // width of the bias-gradient work items (one MN-major swizzle atom)
 
 // ------------------------------------------------------------------ fused dW GEMM + gradient all-reduce over peer memory
 // Data-parallel training: every rank's dW GEMM writes its partial weight gradient into its own copy of the flat
@@ -30,6 +37,7 @@ constexpr int COMM_EXTRA_FLAGS = COMM_MAX_ITEMS * COMM_MAX_WORLD;          // [s
 constexpr int COMM_DONE_FLAGS = COMM_EXTRA_FLAGS + COMM_MAX_WORLD;         // [src rank]: src has broadcast everything it owns
 constexpr int COMM_ITEM_COUNT = COMM_DONE_FLAGS + COMM_MAX_WORLD;          // local: epilogue-warp arrivals per item
 constexpr int COMM_DONE_COUNT = COMM_ITEM_COUNT + COMM_MAX_ITEMS;          // local: comm warps that have finished
+constexpr int COMM_EXTRA_COUNT = COMM_DONE_COUNT + 1;                      // local: epilogue warps of finished bias items
 constexpr int COMM_FLAG_WORDS = COMM_DONE_COUNT + 32;
 constexpr int COMM_ERR_TIMEOUT = 1;
 
@@ -54,6 +62,8 @@ struct GemmArgs {
   CUtensorMap mb[2];  // TN: B operand (weights) per K seg.  NT: X per output segment ([batch][rows][n])
   CUtensorMap md[2];  // TN: md[0] = output.                 NT: output per segment
   CUtensorMap md_row; // TN scatter output: same tensor as md[0] with a one-row box (sample-straddling boxes)
+  CUtensorMap mf;     // NT, bias_items > 0: token-present operand F [batch][rows][GEMM_BIAS_COLS] bf16,
+                      //   F[b, r, i] = 1 if row r of sample b carries a token of stream i (i = 0 audio, 1 video), else 0
   int num_m_blocks;
   int num_n_blocks;
   int bn;  // N tile of this launch: 64 | 128 | 192 | 256 (B tensor-map box rows / atoms must match)
@@ -84,6 +94,13 @@ struct GemmArgs {
   float alpha[2];            // NT: output scale per segment
   float bias_scale[2];       // TN: bias multipliers (fusion_scale folded into the bias)
   int act;                   // 0 = identity, 1 = GELU (erf form)
+  // NT: bias gradients inside the same launch.  bias_items = num_m_blocks appends one GEMM_BIAS_COLS-wide work item
+  // per M block that contracts the dY panel with F:  bias_out[i][h] = bias_alpha[i] * sum_{b, r} dY[b, r, h] * F[b, r, i]
+  // (db of the nn.Linear bias with the pad-after-projection row mask; same fixed reduction order as dW: deterministic).
+  // With comm.world >= 1 the epilogue of the last bias item flags the comm extras (the bias ranges) ready.
+  int bias_items;
+  float* bias_out[2];        // [d_rows] fp32 each, may be null
+  float bias_alpha[2];
   CommArgs comm;             // NT only: world >= 1 fuses the gradient all-reduce into the launch (0: plain GEMM)
 };
 
@@ -96,7 +113,7 @@ int gemm_cta_group();
 int gemm_m_subtiles(int cta_group, GemmMode mode);
 // num_m_blocks counts blocks of cta_group * m_subtiles * GEMM_BM rows; the TN tensor-map boxes must hold
 // m_subtiles * GEMM_BM rows of A and bn / cta_group rows of B
-cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int m_subtiles,
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, GemmOut out, int cta_group, int m_subtiles,
                         int num_sms, cudaStream_t stream);
 // work items (tiles + tail sub-tiles) the launch above will schedule; the fused all-reduce needs <= COMM_MAX_ITEMS
 int gemm_work_items(const GemmArgs& args, int cta_group, int num_sms);
@@ -160,6 +177,27 @@ cudaError_t launch_splice_bwd(const SpliceArgs& args, int num_sms, cudaStream_t 
 cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int64_t dst_ld,
                                int64_t rows, int64_t cols, float alpha, cudaStream_t stream);
 
+// dst_bf16[r, c] = bf16(alpha * src[r, c]); src_dtype is a GemmOut code (bf16 / fp32 / fp16); leading dims in elements
+cudaError_t launch_cast_bf16(const void* src, int src_dtype, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                             int64_t cols, float alpha, cudaStream_t stream);
+
+// Input gradient of the gather for ONE stream (see gather.cu for the forward map): d_feat[b, t, :] = sum of
+// dA[row(b, j), col_off + (t % k) * dim ...] over the tokens j of sample b with j / rep == t / k; zero otherwise.
+struct GatherBwdArgs {
+  const uint8_t* da;          // bf16 [total_rows, a_row_stride]
+  int64_t a_row_stride;       // elements
+  int64_t col_off;            // first column of this stream's segment (elements)
+  uint8_t* dst;               // d_feat [batch][frames][dim], bf16 or fp32
+  int64_t batch_stride;       // bytes
+  int64_t frame_stride;       // bytes
+  int batch, frames, dim;
+  int k, rep;
+  const int32_t* valid;       // [batch] or nullptr
+  const int32_t* tok_offset;  // [batch + 1] or nullptr (uniform tokens_per_sample)
+  int tokens_per_sample;
+};
+cudaError_t launch_gather_bwd(const GatherBwdArgs& args, bool out_f32, cudaStream_t stream);
+
 // Column sums of dY over flagged rows, deterministic two-pass:
 //   out0[c] = alpha0 * sum_{r : flag bit0} dY[r, c],  out1[c] = alpha1 * sum_{r : flag bit1} dY[r, c]
 struct ColsumArgs {
@@ -192,7 +230,7 @@ cudaError_t launch_colsum(const ColsumArgs& args, cudaStream_t stream);
 struct ResampleArgs {
   const uint8_t* x;   // [batch, src_rows, hidden]
   uint8_t* out;       // [batch, dst_rows, hidden]
-  int elem_size;      // 2 = bf16, 4 = fp32
+  int dtype;          // GemmOut code: bf16, fp32 or fp16 (accumulation is fp32)
   int batch, src_rows, dst_rows, hidden;
   const int32_t* row_ptr;  // [dst_rows + 1]
   const int32_t* col;      // [nnz] source row index

@@ -3,6 +3,8 @@
 //   colsum      : db = alpha * sum over flagged rows of dY   (autograd of the nn.Linear bias,
 //                 modality_connector.py:32, with the pad-after-projection row mask of
 //                 clip_whisper_model.py:340-345)
+#include <cuda_fp16.h>
+
 #include "avc_kernels.h"
 #include "avc_ptx.cuh"
 
@@ -169,8 +171,9 @@ __global__ void __launch_bounds__(CS_THREADS, 4) colsum_kernel(const __grid_cons
 }
 
 // out[b, i, :] = sum_{t in [row_ptr[i], row_ptr[i+1])} weight[t] * x[b, col[t], :]   (fp32 accumulate)
-template <bool F32>
+template <int DT>  // GemmOut code of the element type
 __global__ void __launch_bounds__(128) row_resample_kernel(const __grid_constant__ ResampleArgs a) {
+  constexpr bool F32 = DT == GEMM_OUT_F32;
   const int i = blockIdx.x, b = blockIdx.y;
   const int t0 = __ldg(a.row_ptr + i), t1 = __ldg(a.row_ptr + i + 1);
   constexpr int EPV = F32 ? 4 : 8;  // elements per 16-byte vector
@@ -192,14 +195,24 @@ __global__ void __launch_bounds__(128) row_resample_kernel(const __grid_constant
                                static_cast<uint32_t>(q.z), static_cast<uint32_t>(q.w)};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          acc[2 * e + 0] = fmaf(w, __uint_as_float(u[e] << 16), acc[2 * e + 0]);
-          acc[2 * e + 1] = fmaf(w, __uint_as_float(u[e] & 0xffff0000u), acc[2 * e + 1]);
+          float lo, hi;
+          if (DT == GEMM_OUT_F16) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
+            lo = f.x; hi = f.y;
+          } else {
+            lo = __uint_as_float(u[e] << 16); hi = __uint_as_float(u[e] & 0xffff0000u);
+          }
+          acc[2 * e + 0] = fmaf(w, lo, acc[2 * e + 0]);
+          acc[2 * e + 1] = fmaf(w, hi, acc[2 * e + 1]);
         }
       }
     }
     int4 o;
     if (F32) {
       o = make_int4(__float_as_int(acc[0]), __float_as_int(acc[1]), __float_as_int(acc[2]), __float_as_int(acc[3]));
+    } else if (DT == GEMM_OUT_F16) {
+      o = make_int4(static_cast<int>(pack_f16x2(acc[0], acc[1])), static_cast<int>(pack_f16x2(acc[2], acc[3])),
+                    static_cast<int>(pack_f16x2(acc[4], acc[5])), static_cast<int>(pack_f16x2(acc[6], acc[7])));
     } else {
       o = make_int4(static_cast<int>(pack_bf16x2(acc[0], acc[1])), static_cast<int>(pack_bf16x2(acc[2], acc[3])),
                     static_cast<int>(pack_bf16x2(acc[4], acc[5])), static_cast<int>(pack_bf16x2(acc[6], acc[7])));
@@ -267,6 +280,110 @@ __global__ void __launch_bounds__(256) pack_weight_t_kernel(const float* __restr
       const float x = tile[tx][i];
       const uint32_t b = pack_bf16x2(x, 0.f);
       reinterpret_cast<uint16_t*>(dst)[c * dst_ld + r] = static_cast<uint16_t>(b & 0xffffu);
+    }
+  }
+}
+
+
+// dst_bf16[r, c] = bf16(alpha * src[r, c]) for fp32 / fp16 / bf16 sources: the cast of the connector input to the
+// compute dtype (modality_connector.py:18-19) and of an fp16 / fp32 upstream gradient to the dW GEMM's operand type.
+// One thread = 8 consecutive columns (16-byte store).
+template <int SRC>  // GemmOut code of the source element type
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const uint8_t* __restrict__ src, int64_t src_ld,
+                                                        uint8_t* __restrict__ dst, int64_t dst_ld, int64_t rows,
+                                                        int64_t cols, float alpha) {
+  const int64_t groups_per_row = cols >> 3;
+  const int64_t total = rows * groups_per_row;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / groups_per_row;
+    const int64_t c = (g - r * groups_per_row) << 3;
+    float x[8];
+    if (SRC == GEMM_OUT_F32) {
+      const float* sp = reinterpret_cast<const float*>(src) + r * src_ld + c;
+      const int4 a = ld_nc_v4(sp), b = ld_nc_v4(sp + 4);
+      x[0] = __int_as_float(a.x); x[1] = __int_as_float(a.y); x[2] = __int_as_float(a.z); x[3] = __int_as_float(a.w);
+      x[4] = __int_as_float(b.x); x[5] = __int_as_float(b.y); x[6] = __int_as_float(b.z); x[7] = __int_as_float(b.w);
+    } else {
+      const int4 q = ld_nc_v4(src + (r * src_ld + c) * 2);
+      const uint32_t w[4] = {static_cast<uint32_t>(q.x), static_cast<uint32_t>(q.y), static_cast<uint32_t>(q.z),
+                             static_cast<uint32_t>(q.w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (SRC == GEMM_OUT_F16) {
+          const __half2 h = *reinterpret_cast<const __half2*>(&w[e]);
+          const float2 f = __half22float2(h);
+          x[2 * e] = f.x; x[2 * e + 1] = f.y;
+        } else {
+          x[2 * e] = __uint_as_float(w[e] << 16); x[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        }
+      }
+    }
+    int4 o;
+    o.x = static_cast<int>(pack_bf16x2(x[0] * alpha, x[1] * alpha));
+    o.y = static_cast<int>(pack_bf16x2(x[2] * alpha, x[3] * alpha));
+    o.z = static_cast<int>(pack_bf16x2(x[4] * alpha, x[5] * alpha));
+    o.w = static_cast<int>(pack_bf16x2(x[6] * alpha, x[7] * alpha));
+    st_na_v4(dst + (r * dst_ld + c) * 2, o);
+  }
+}
+
+// Input gradient of the gather (align + stack + concat): every frame (b, t) of one stream receives the sum of the
+// column slices of dA rows that read it -- token j reads the stack j / rep, i.e. frames k * (j / rep) .. + k - 1 --
+// and zero when no token does (t past the valid length or past the token cap).  One warp per frame, 16-byte vectors.
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) gather_bwd_kernel(const __grid_constant__ GatherBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t total = static_cast<int64_t>(a.batch) * a.frames;
+  const int nvec = a.dim >> 3;  // 8 bf16 per 16-byte source vector
+  for (int64_t f = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); f < total; f += warps) {
+    const int b = static_cast<int>(f / a.frames);
+    const int t = static_cast<int>(f - static_cast<int64_t>(b) * a.frames);
+    int len = a.frames;
+    if (a.valid != nullptr) {
+      const int l = __ldg(a.valid + b);
+      len = l < len ? (l < 0 ? 0 : l) : len;
+    }
+    int64_t row0;
+    int ntok;
+    if (a.tok_offset != nullptr) {
+      row0 = __ldg(a.tok_offset + b);
+      ntok = __ldg(a.tok_offset + b + 1) - static_cast<int>(row0);
+    } else {
+      row0 = static_cast<int64_t>(b) * a.tokens_per_sample;
+      ntok = a.tokens_per_sample;
+    }
+    const int s = t / a.k;                   // stack index
+    const int slot = t - s * a.k;            // position inside the stack
+    int j0 = s * a.rep, j1 = j0 + a.rep;     // tokens that read this stack
+    j1 = j1 < ntok ? j1 : ntok;
+    if (t >= len) j1 = j0;                   // zero-padded in the forward: no gradient
+    uint8_t* out = a.dst + b * a.batch_stride + t * a.frame_stride;
+    for (int v = lane; v < nvec; v += 32) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = j0; j < j1; ++j) {
+        const int4 q = ld_nc_v4(a.da + ((row0 + j) * a.a_row_stride + a.col_off + static_cast<int64_t>(slot) * a.dim +
+                                        static_cast<int64_t>(v) * 8) * 2);
+        const uint32_t w[4] = {static_cast<uint32_t>(q.x), static_cast<uint32_t>(q.y), static_cast<uint32_t>(q.z),
+                               static_cast<uint32_t>(q.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += __uint_as_float(w[e] << 16);
+          acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+        }
+      }
+      if (OUT_F32) {
+        float* o = reinterpret_cast<float*>(out) + static_cast<int64_t>(v) * 8;
+        st_na_v4(o, make_int4(__float_as_int(acc[0]), __float_as_int(acc[1]), __float_as_int(acc[2]),
+                              __float_as_int(acc[3])));
+        st_na_v4(o + 4, make_int4(__float_as_int(acc[4]), __float_as_int(acc[5]), __float_as_int(acc[6]),
+                                  __float_as_int(acc[7])));
+      } else {
+        st_na_v4(out + static_cast<int64_t>(v) * 16,
+                 make_int4(static_cast<int>(pack_bf16x2(acc[0], acc[1])), static_cast<int>(pack_bf16x2(acc[2], acc[3])),
+                           static_cast<int>(pack_bf16x2(acc[4], acc[5])), static_cast<int>(pack_bf16x2(acc[6], acc[7]))));
+      }
     }
   }
 }
@@ -407,14 +524,15 @@ cudaError_t launch_adamw(const AdamWArgs& a, cudaStream_t stream) {
 
 cudaError_t launch_row_resample(const ResampleArgs& a, cudaStream_t stream) {
   if (a.batch <= 0 || a.dst_rows <= 0) return cudaSuccess;
-  const int epv = a.elem_size == 4 ? 4 : 8;
+  const int epv = a.dtype == GEMM_OUT_F32 ? 4 : 8;
   if (a.hidden % epv != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
     return cudaErrorMisalignedAddress;
   if (a.batch > 65535) return cudaErrorInvalidValue;
   dim3 grid(a.dst_rows, a.batch);
-  if (a.elem_size == 4) row_resample_kernel<true><<<grid, 128, 0, stream>>>(a);
-  else row_resample_kernel<false><<<grid, 128, 0, stream>>>(a);
+  if (a.dtype == GEMM_OUT_F32) row_resample_kernel<GEMM_OUT_F32><<<grid, 128, 0, stream>>>(a);
+  else if (a.dtype == GEMM_OUT_F16) row_resample_kernel<GEMM_OUT_F16><<<grid, 128, 0, stream>>>(a);
+  else row_resample_kernel<GEMM_OUT_BF16><<<grid, 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -429,6 +547,50 @@ cudaError_t launch_pack_weight(const float* src, int64_t src_ld, void* dst, int6
   if (grid > 148 * 16) grid = 148 * 16;
   pack_weight_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
       src, src_ld, static_cast<uint8_t*>(dst), dst_ld, rows, cols, alpha);
+  return cudaGetLastError();
+}
+
+
+cudaError_t launch_cast_bf16(const void* src, int src_dtype, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                             int64_t cols, float alpha, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  const int es = src_dtype == GEMM_OUT_F32 ? 4 : 2;
+  if (cols % 8 != 0 || (src_ld * es) % 16 != 0 || dst_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(dst) & 15) != 0)
+    return cudaErrorMisalignedAddress;
+  const int64_t total = rows * (cols >> 3);
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  const uint8_t* s8 = static_cast<const uint8_t*>(src);
+  uint8_t* d8 = static_cast<uint8_t*>(dst);
+  switch (src_dtype) {
+    case GEMM_OUT_F32:
+      cast_bf16_kernel<GEMM_OUT_F32><<<static_cast<int>(grid), 256, 0, stream>>>(s8, src_ld, d8, dst_ld, rows, cols, alpha);
+      break;
+    case GEMM_OUT_F16:
+      cast_bf16_kernel<GEMM_OUT_F16><<<static_cast<int>(grid), 256, 0, stream>>>(s8, src_ld, d8, dst_ld, rows, cols, alpha);
+      break;
+    case GEMM_OUT_BF16:
+      cast_bf16_kernel<GEMM_OUT_BF16><<<static_cast<int>(grid), 256, 0, stream>>>(s8, src_ld, d8, dst_ld, rows, cols, alpha);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_bwd(const GatherBwdArgs& a, bool out_f32, cudaStream_t stream) {
+  if (a.batch <= 0 || a.frames <= 0) return cudaSuccess;
+  const int es = out_f32 ? 4 : 2;
+  if (a.dim % 8 != 0 || a.k < 1 || a.rep < 1 || (reinterpret_cast<uintptr_t>(a.da) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(a.dst) & 15) != 0 || a.a_row_stride % 8 != 0 || a.col_off % 8 != 0 ||
+      a.batch_stride % 16 != 0 || a.frame_stride % 16 != 0 || a.frame_stride < static_cast<int64_t>(a.dim) * es)
+    return cudaErrorMisalignedAddress;
+  const int64_t total = static_cast<int64_t>(a.batch) * a.frames;
+  int64_t grid = (total + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (out_f32) gather_bwd_kernel<true><<<static_cast<int>(grid), 256, 0, stream>>>(a);
+  else gather_bwd_kernel<false><<<static_cast<int>(grid), 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

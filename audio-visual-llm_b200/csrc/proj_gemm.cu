@@ -2,6 +2,7 @@
 //
 //   forward  (GEMM_TN):  Y[b, r, n] = act( sum_seg  A_seg[b, r, :] . W_seg[n, :]  + flag0*bias0[n] + flag1*bias1[n] )
 //   backward (GEMM_NT):  dW_seg[h, k] = alpha_seg * sum_{b, r} dY[b, r, h] * X_seg[b, r, k]
+//                        db_i[h]      = alpha_i   * sum_{b, r} dY[b, r, h] * F[b, r, i]      ("bias items", same launch)
 //
 // This replaces the two nn.Linear calls + pad + weighted sum of the reference
 // (modality_connector.py:43-44, clip_whisper_model.py:424-434) and their autograd dW.
@@ -174,9 +175,10 @@ __device__ __forceinline__ void comm_reduce(const CommArgs& cm, int64_t base, in
   else comm_reduce_rows<COMM_MAX_WORLD, true>(cm, base, ld, rows, nvec, lane);
 }
 
-template <int MODE, bool OUT_F32, int CG, int MT, int COMM>
+template <int MODE, int OUT, int CG, int MT, int COMM>
 __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
   using C = Cfg<CG, MT>;
+  constexpr bool OUT_F32 = OUT == GEMM_OUT_F32;
   constexpr int kStages = C::kStages;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
   constexpr int A_BYTES = C::A_BYTES;
@@ -242,10 +244,21 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
   const int full_tiles = args.full_tiles;
   const int tail_split = args.tail_split;
   const int total_work = full_tiles + (num_tiles - full_tiles) * tail_split;
-  auto decode = [&](int w, int& m_blk, int& n_blk, int& n_off, int& width) {
+  // dW only: after the tiles, one GEMM_BIAS_COLS-wide "bias item" per M block contracts the same dY panel with the
+  // token-present operand F instead of X -> columns 0 / 1 of its accumulator are the bias gradients of that M block.
+  // They are the shortest items of the list and sit at its end, where the last (partial) round has idle workers.
+  const int all_work = total_work + (MODE == GEMM_NT ? args.bias_items : 0);
+  // returns true for a bias item
+  auto decode = [&](int w, int& m_blk, int& n_blk, int& n_off, int& width) -> bool {
     int tile = w;
     n_off = 0;
     width = bn;
+    if (MODE == GEMM_NT && w >= total_work) {
+      m_blk = w - total_work;
+      n_blk = 0;
+      width = GEMM_BIAS_COLS;
+      return true;
+    }
     if (w >= full_tiles) {
       const int u = w - full_tiles;
       tile = full_tiles + u / tail_split;
@@ -262,6 +275,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     const int r = tile - g * per_group;
     m_blk = first_m + r % rows_in_group;
     n_blk = r / rows_in_group;
+    return false;
   };
   // bytes this CTA's TMA loads deliver per stage (OOB parts of a box are zero-filled and still counted)
   const uint32_t cta_tx = A_BYTES + (MODE == GEMM_TN ? static_cast<uint32_t>(bn_cta) * (BK * 2)
@@ -281,9 +295,9 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       // forward: activations stream through once per N sweep, the weights are re-read by every M block
       const uint64_t pol_a = args.l2_hints ? (MODE == GEMM_TN ? kEvictFirst : kEvictNormal) : kEvictNormal;
       const uint64_t pol_b = args.l2_hints ? (MODE == GEMM_TN ? kEvictLast : kEvictNormal) : kEvictNormal;
-      for (int w = worker; w < total_work; w += num_workers) {
+      for (int w = worker; w < all_work; w += num_workers) {
         int m_blk, n_blk, n_off, width;
-        decode(w, m_blk, n_blk, n_off, width);
+        const bool bias = decode(w, m_blk, n_blk, n_off, width);
         const int w_cta = width / CG;  // B rows / columns of this CTA that the MMA reads
         if (MODE == GEMM_TN) {
           const int b = m_blk / args.m_tiles_per_batch;
@@ -301,21 +315,25 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           }
         } else {
           const int m0 = m_blk * TILE_M + static_cast<int>(rank) * (BM * MT);
-          const int seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
-          const int nl0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off + static_cast<int>(rank) * w_cta;
+          const int seg = (!bias && n_blk >= args.n_blocks_seg0) ? 1 : 0;
+          const int nl0 = bias ? static_cast<int>(rank) * w_cta
+                               : (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off + static_cast<int>(rank) * w_cta;
+          // bias item: the B operand is one 64-wide atom of F (columns past GEMM_BIAS_COLS are zero-filled by TMA)
+          const CUtensorMap* mapb = bias ? &args.mf : &args.mb[seg];
+          const int nbx = bias ? 1 : nb_boxes;
+          const uint32_t tx = bias ? (A_BYTES + MN_ATOM_BYTES) : cta_tx;
           for (int bb = 0; bb < args.red_batches; ++bb) {
             for (int kb = 0; kb < args.red_kblocks_per_batch; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              if (leader) mbar_arrive_expect_tx(full_bar(stage), cta_tx * CG);
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), tx * CG);
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               const int row = kb * BK;
 #pragma unroll
               for (int i = 0; i < BM * MT / 64; ++i)
                 load(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64, args.a_row_base + row, bb,
                      pol_a);
-              for (int i = 0; i < nb_boxes; ++i)
-                load(sa + A_BYTES + i * MN_ATOM_BYTES, &args.mb[seg], full_bar(stage), nl0 + i * 64, row, bb,
-                     pol_b);
+              for (int i = 0; i < nbx; ++i)
+                load(sa + A_BYTES + i * MN_ATOM_BYTES, mapb, full_bar(stage), nl0 + i * 64, row, bb, pol_b);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     // ======================================================================= MMA issuer (leader CTA only)
     if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int w = worker; w < total_work; w += num_workers) {
+      for (int w = worker; w < all_work; w += num_workers) {
         int m_blk, n_blk, n_off, width;
         decode(w, m_blk, n_blk, n_off, width);
         const uint32_t idesc = make_idesc_bf16(BM * CG, width, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
@@ -380,10 +398,10 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     const int ew = warp - 2;   // staging buffer owner index
     constexpr int COLS = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
     uint32_t acc = 0, acc_phase = 0, buf = 0;
-    for (int w = worker; w < total_work; w += num_workers) {
+    for (int w = worker; w < all_work; w += num_workers) {
       int m_blk, n_blk, n_off, width;
-      decode(w, m_blk, n_blk, n_off, width);
-      const int nchunk = width / COLS;
+      const bool bias = decode(w, m_blk, n_blk, n_off, width);
+      const int nchunk = bias ? 0 : width / COLS;
       int tile_row0, out_batch, out_col0, seg = 0;
       if (MODE == GEMM_TN) {
         out_batch = m_blk / args.m_tiles_per_batch;
@@ -392,7 +410,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       } else {
         out_batch = 0;
         tile_row0 = m_blk * TILE_M + static_cast<int>(rank) * (BM * MT) + q * 32;
-        seg = (n_blk >= args.n_blocks_seg0) ? 1 : 0;
+        seg = (!bias && n_blk >= args.n_blocks_seg0) ? 1 : 0;
         out_col0 = (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off;
       }
       const float alpha = args.alpha[seg];
@@ -421,6 +439,16 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
         if (args.bias1 == nullptr) f1 = 0.f;
       }
       const uint32_t t_row = tmem_base + (MT == 2 ? h * BN : acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
+      if (MODE == GEMM_NT && bias) {
+        // bias item: accumulator column i of this thread's row h is sum_r dY[r, h] * F[r, i]
+        uint32_t v0[32];
+        tmem_ld_32x32(t_row, v0);
+        tmem_ld_wait();
+        if (my_row < args.d_rows) {
+          if (args.bias_out[0] != nullptr) args.bias_out[0][my_row] = args.bias_alpha[0] * __uint_as_float(v0[0]);
+          if (args.bias_out[1] != nullptr) args.bias_out[1][my_row] = args.bias_alpha[1] * __uint_as_float(v0[1]);
+        }
+      }
 
 #pragma unroll 1
       for (int c = 0; c < nchunk; ++c) {
@@ -479,8 +507,12 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
                          __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
           } else {
             const int o = (8 * j) % COLS;  // (COLS == 64 here)
-            st_shared_v4(dst, pack_bf16x2(x[o + 0], x[o + 1]), pack_bf16x2(x[o + 2], x[o + 3]),
-                         pack_bf16x2(x[o + 4], x[o + 5]), pack_bf16x2(x[o + 6], x[o + 7]));
+            if (OUT == GEMM_OUT_F16)
+              st_shared_v4(dst, pack_f16x2(x[o + 0], x[o + 1]), pack_f16x2(x[o + 2], x[o + 3]),
+                           pack_f16x2(x[o + 4], x[o + 5]), pack_f16x2(x[o + 6], x[o + 7]));
+            else
+              st_shared_v4(dst, pack_bf16x2(x[o + 0], x[o + 1]), pack_bf16x2(x[o + 2], x[o + 3]),
+                           pack_bf16x2(x[o + 4], x[o + 5]), pack_bf16x2(x[o + 6], x[o + 7]));
           }
         }
         fence_proxy_async_smem();
@@ -517,7 +549,24 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
-      if (COMM != 0) {
+      if (COMM != 0 && bias) {
+        // The bias gradients of this rank are complete once every epilogue warp of every bias item has stored its
+        // rows (plain stores): the last of them flags the extra ranges ready at every rank that owns a chunk of them.
+        if (lane == 0) {
+          const CommArgs& cm = args.comm;
+          __threadfence();
+          uint32_t* lf = cm.flags[cm.rank];
+          const uint32_t expect = static_cast<uint32_t>(EPI_WARPS * CG * args.bias_items);
+          if (atomicAdd(lf + COMM_EXTRA_COUNT, 1u) == expect - 1) {
+            atomicExch(lf + COMM_EXTRA_COUNT, 0u);
+            __threadfence_system();
+            const int nch = ((cm.extra_len[0] + 127) >> 7) + ((cm.extra_len[1] + 127) >> 7);
+            for (int p = 0; p < cm.world && p < nch; ++p)
+              st_relaxed_sys_u32(cm.flags[p] + COMM_EXTRA_FLAGS + cm.rank, cm.epoch);
+          }
+        }
+        __syncwarp();
+      } else if (COMM != 0) {
         // This warp's part of work item w is in the local bucket once its TMA stores have completed.  The last of the
         // item's EPI_WARPS x CG epilogue warps tells the item's owner rank that this rank's partial tile is ready.
         if (lane == 0) {
@@ -662,11 +711,15 @@ int plan_schedule(GemmArgs& args, GemmMode mode, int num_sms) {
 }
 
 template <int CG, int MT>
-cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int num_sms, cudaStream_t stream) {
+cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, GemmOut out, int num_sms, cudaStream_t stream) {
   GemmArgs args = args_in;
   const int workers = plan_schedule<CG>(args, mode, num_sms);
   const bool comm = args.comm.world > 0;
+  const bool out_fp32 = out == GEMM_OUT_F32;
   if (comm && !(mode == GEMM_NT && out_fp32 && CG == 2)) return cudaErrorInvalidValue;
+  if (mode != GEMM_NT && args.bias_items != 0) return cudaErrorInvalidValue;
+  if (mode == GEMM_NT && out == GEMM_OUT_F16) return cudaErrorInvalidValue;
+  if (args.bias_items != 0 && args.bias_items != args.num_m_blocks) return cudaErrorInvalidValue;
   args.comm.poll_ns = static_cast<uint32_t>(env_int("AVC_COMM_POLL_NS", 200));
   auto run = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG, MT>::SMEM_ALLOC);
@@ -687,19 +740,23 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, bool out_fp32, int
   };
   if constexpr (CG == 2) {
     if (comm) {
-      if (args.comm.mc != nullptr) return run(gemm_kernel<GEMM_NT, true, CG, MT, COMM_MC>);
+      if (args.comm.mc != nullptr) return run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, COMM_MC>);
       switch (args.comm.world) {
-        case 1: return run(gemm_kernel<GEMM_NT, true, CG, MT, 1>);
-        case 2: return run(gemm_kernel<GEMM_NT, true, CG, MT, 2>);
-        case 4: return run(gemm_kernel<GEMM_NT, true, CG, MT, 4>);
-        case 8: return run(gemm_kernel<GEMM_NT, true, CG, MT, 8>);
-        default: return run(gemm_kernel<GEMM_NT, true, CG, MT, -1>);
+        case 1: return run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, 1>);
+        case 2: return run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, 2>);
+        case 4: return run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, 4>);
+        case 8: return run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, 8>);
+        default: return run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, -1>);
       }
     }
   }
-  if (mode == GEMM_TN)
-    return out_fp32 ? run(gemm_kernel<GEMM_TN, true, CG, MT, 0>) : run(gemm_kernel<GEMM_TN, false, CG, MT, 0>);
-  return out_fp32 ? run(gemm_kernel<GEMM_NT, true, CG, MT, 0>) : run(gemm_kernel<GEMM_NT, false, CG, MT, 0>);
+  if (mode == GEMM_TN) {
+    if (out == GEMM_OUT_F32) return run(gemm_kernel<GEMM_TN, GEMM_OUT_F32, CG, MT, 0>);
+    if (out == GEMM_OUT_F16) return run(gemm_kernel<GEMM_TN, GEMM_OUT_F16, CG, MT, 0>);
+    return run(gemm_kernel<GEMM_TN, GEMM_OUT_BF16, CG, MT, 0>);
+  }
+  return out_fp32 ? run(gemm_kernel<GEMM_NT, GEMM_OUT_F32, CG, MT, 0>)
+                  : run(gemm_kernel<GEMM_NT, GEMM_OUT_BF16, CG, MT, 0>);
 }
 
 __global__ void comm_signal_extra_kernel(const __grid_constant__ CommArgs cm) {
@@ -765,14 +822,14 @@ cudaError_t launch_comm_signal_extra(const CommArgs& comm, cudaStream_t stream) 
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, bool out_fp32, int cta_group, int m_subtiles,
+cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, GemmOut out, int cta_group, int m_subtiles,
                         int num_sms, cudaStream_t stream) {
   const int num_tiles = args.num_m_blocks * args.num_n_blocks;
   if (num_tiles <= 0) return cudaSuccess;
   if (args.bn < 64 || args.bn > BN || args.bn % 64 != 0) return cudaErrorInvalidValue;
-  if (cta_group == 2 && m_subtiles == 2) return launch_cg<2, 2>(args, mode, out_fp32, num_sms, stream);
-  if (cta_group == 2) return launch_cg<2, 1>(args, mode, out_fp32, num_sms, stream);
-  return launch_cg<1, 1>(args, mode, out_fp32, num_sms, stream);
+  if (cta_group == 2 && m_subtiles == 2) return launch_cg<2, 2>(args, mode, out, num_sms, stream);
+  if (cta_group == 2) return launch_cg<2, 1>(args, mode, out, num_sms, stream);
+  return launch_cg<1, 1>(args, mode, out, num_sms, stream);
 }
 
 }  // namespace avc

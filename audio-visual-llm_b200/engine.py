@@ -2,7 +2,7 @@
 fwd + bwd, with every buffer pre-allocated (no allocator traffic, CUDA-graph friendly).
 
     pack weights -> gather -> projector GEMM -> splice (+masks)          forward
-    splice-bwd -> dW GEMM -> bias column sums [-> grad all-reduce]       backward
+    splice-bwd -> dW GEMM (+ db work items) [-> grad all-reduce]         backward
 
 This is the same kernel sequence `connector_ops._FusedConnectorFn` runs under autograd; the engine exists so
 the data-parallel trainer (and bench.py) can drive it without per-step Python allocation.  The projector
@@ -39,7 +39,11 @@ class StepShape:
 
 class ConnectorStep:
     def __init__(self, shape: StepShape, plan: FusePlan, device, out_dtype=torch.bfloat16, seed: int = 0,
-                 process_group=None, fuse_gather: bool = True, fused_allreduce: Optional[bool] = None):
+                 process_group=None, fuse_gather: bool = True, fused_allreduce: Optional[bool] = None,
+                 ragged_range: Optional[tuple] = None, ragged_seed: int = 4):
+        """ragged_range=(lo, hi): variable-length placeholders (BASELINE configs[3]) -- every sample gets a valid frame
+        count drawn from U{lo..hi} (seed `ragged_seed`) for each stream, contributes tokens(len) fused tokens, and its
+        id row is `[prompt | that many placeholders | pad]`; the step then runs gather -> GEMM -> ragged splice."""
         if out_dtype != torch.bfloat16:
             raise L.ConnectorError("the step engine runs the bf16 training configuration")
         L.require_device(torch.device(device).index or 0)
@@ -50,6 +54,25 @@ class ConnectorStep:
         self.sa, self.sv = p.scales(self.use_a, self.use_v)
         self.N = p.tokens(s.audio_frames if self.use_a else None, s.video_frames if self.use_v else None)
         self.M = s.batch * self.N
+        self.ragged = ragged_range is not None
+        self.audio_valid = self.video_valid = self.tok_offset = None
+        self.counts = [self.N] * s.batch
+        if self.ragged:
+            from .connector_ops import ragged_token_offsets
+
+            gr = torch.Generator(device="cpu").manual_seed(ragged_seed)
+            lo, hi = ragged_range
+
+            def draw(T):
+                return torch.randint(lo, min(hi, T) + 1, (s.batch,), generator=gr).tolist()
+
+            la = draw(s.audio_frames) if self.use_a else None
+            lv = draw(s.video_frames) if self.use_v else None
+            self.lengths_host = (la, lv)
+            self.tok_offset, self.audio_valid, self.video_valid, self.M = ragged_token_offsets(
+                p, s.batch, s.audio_frames if self.use_a else None, s.video_frames if self.use_v else None, la, lv, dev)
+            offs = self.tok_offset.tolist()
+            self.counts = [offs[i + 1] - offs[i] for i in range(s.batch)]
         self.Ka = p.audio_stride * s.audio_dim if self.use_a else 0
         self.Kv = p.video_stride * s.video_dim if self.use_v else 0
         self.K = self.Ka + self.Kv
@@ -87,12 +110,10 @@ class ConnectorStep:
             fused_allreduce = False  # the flag layout holds COMM_MAX_WORLD ranks; larger jobs all-reduce through NCCL
         self.fused_allreduce = bool(fused_allreduce)
         # Transport of the fused all-reduce: an NVSwitch multicast mapping of the buckets (multimem.ld_reduce adds in the
-        # switch, multimem.st writes every rank) instead of peer loads / stores.  Default for <= 4 ranks, where it was
-        # verified and measured this round (N = 4: 0.96 vs 1.02 ms / step); AVC_COMM_MULTIMEM=1 / 0 forces it on / off.
+        # switch, multimem.st writes every rank) instead of peer loads / stores: (1 + 1 / world) x the bucket per GPU and
+        # direction instead of 2 (world - 1) / world x.  AVC_COMM_MULTIMEM=0 selects the peer transport.
         # Falls back to the peer mapping, on all ranks alike, when multicast objects are not available.
-        world_ = dist.get_world_size(process_group) if ddp else 1
-        multimem = self.fused_allreduce and \
-            os.environ.get("AVC_COMM_MULTIMEM", "1" if world_ <= 4 else "0") == "1"
+        multimem = self.fused_allreduce and os.environ.get("AVC_COMM_MULTIMEM", "1") == "1"
         try:
             self.bucket = GradBucket(sizes, dev, process_group=process_group, peer=self.fused_allreduce,
                                      multimem=multimem)
@@ -108,6 +129,9 @@ class ConnectorStep:
         self.video = randn(s.batch, s.video_frames, s.video_dim).to(bf).to(dev) if self.use_v else None
         prompt = torch.randint(1, s.vocab, (s.batch, s.prompt_len), generator=g)
         ph = torch.full((s.batch, self.N), self.placeholder_id, dtype=torch.int64)
+        if self.ragged:  # right-padded: the placeholders of sample b end after counts[b] positions, pad id 0 follows
+            for b_, c_ in enumerate(self.counts):
+                ph[b_, c_:] = 0
         self.input_ids = torch.cat([prompt, ph], 1).to(dev)
         labels = torch.randint(1, s.vocab, (s.batch, s.label_len), generator=g)
         labels[:, s.label_len * 3 // 4:] = 0  # pad tail (pad id 0)
@@ -125,7 +149,12 @@ class ConnectorStep:
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.dY = torch.empty(self.M, H, dtype=bf, device=dev)
         self.colsum_ws = L.colsum_workspace(H, dev)
+        # db comes out of the dW GEMM launch (64-wide work items that contract the dY panels with the token-present
+        # operand); AVC_BIAS_IN_GEMM=0 runs the stand-alone column-sum kernel next to the GEMM instead
+        self.bias_in_gemm = os.environ.get("AVC_BIAS_IN_GEMM", "1") != "0"
+        self._present = None
         self.sp = L.make_splice(self.input_ids, self.placeholder_id, 0, H, tokens_per_sample=self.N,
+                                tok_offset=self.tok_offset,
                                 embed_table=self.embed_table, attention_mask=self.mask, mask_mode=p.mask_mode,
                                 label_mode=p.label_mode, labels_in=self.labels_in, labels_out=self.labels_out,
                                 status=self.status)
@@ -141,11 +170,12 @@ class ConnectorStep:
         # rows P .. P+N-1).  Otherwise: gather -> GEMM, splice-bwd -> GEMM.
         def free(frames, k):
             return frames % k == 0 and frames // k == self.N
-        self.direct = bool(fuse_gather and p.audio_repeat == 1 and p.video_repeat == 1
+        self.direct = bool(fuse_gather and not self.ragged and p.audio_repeat == 1 and p.video_repeat == 1
                            and (not self.use_a or free(s.audio_frames, p.audio_stride))
                            and (not self.use_v or free(s.video_frames, p.video_stride)))
         npack = int(self.use_a) + int(self.use_v)
-        self.launches_per_step = npack + (3 if self.direct else 5) + 1  # packs + {[gather] gemm splice [splice_bwd] gemm} + colsum
+        # packs + {[gather] gemm splice [splice_bwd] gemm} [+ colsum]
+        self.launches_per_step = npack + (3 if self.direct else 5) + (0 if self.bias_in_gemm else 1)
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
         self.nvtx = os.environ.get("AVC_NVTX", "0") == "1"
         # N > 1: optionally all-reduce the audio-weight span while the video-weight dW launch still runs.  Measured on
@@ -234,6 +264,8 @@ class ConnectorStep:
         if not self.direct:
             self._timed("gather", lambda: L.gather_fwd(self.audio, self.video, p.audio_stride, p.video_stride,
                                                        self.shape.batch, self.N, self.A, self.flags,
+                                                       tok_offset=self.tok_offset, audio_valid=self.audio_valid,
+                                                       video_valid=self.video_valid,
                                                        audio_repeat=p.audio_repeat, video_repeat=p.video_repeat))
         if self.use_a and self.use_v:
             b0, b1, s0, s1 = self.ba, self.bv, self.sa, self.sv
@@ -264,8 +296,10 @@ class ConnectorStep:
         g = self.bucket
         B, N, P = self.shape.batch, self.N, self.shape.prompt_len
         # data parallel: the 1 / world factor of the gradient mean is folded into the dW / bias-sum epilogues, so the
-        # collective is a plain SUM (NVLS-capable) instead of AVG
-        inv = 1.0 / g.world_size() if (allreduce and self.prescale_grads) else 1.0
+        # collective is a plain SUM (NVLS-capable) instead of AVG.  The fused launch only sums, so it always pre-scales
+        # (AVC_PRESCALE_GRADS=0 switches the NCCL schedules to ReduceOp.AVG): either way bucket.flat ends as the MEAN.
+        fused = allreduce and self.fused_allreduce
+        inv = 1.0 / g.world_size() if (allreduce and (self.prescale_grads or fused)) else 1.0
         ga, gv = self.sa * inv, self.sv * inv
         pre = inv != 1.0
         dba = g["audio_connector.linear.bias"] if self.use_a else None
@@ -281,11 +315,20 @@ class ConnectorStep:
             xa = self.A[:, :self.Ka] if self.use_a else None
             xv = self.A[:, self.Ka:] if self.use_v else None
             cs = dict(row_flags=self.flags)
-        if allreduce and self.fused_allreduce:
-            return self._backward_fused_allreduce(dy, base, xa, xv, dba, dbv, ga, gv, cs)
+        bias = None
+        if self.bias_in_gemm:
+            if self.direct:
+                present = L.present_operand(B, N, self.device)
+            else:
+                if self._present is None:  # static engine: the gather writes the same flags every step
+                    self._present = L.present_operand(1, self.M, self.device, row_flags=self.flags)
+                present = self._present
+            bias = (present, dba, dbv, ga, gv)
+        if fused:
+            return self._backward_fused_allreduce(dy, base, xa, xv, dba, dbv, ga, gv, cs, bias)
         overlap = allreduce and self.overlap_comm and g.world_size() > 1 and self.use_a and self.use_v
         # the bias column sums only read d(inputs_embeds): run them under the dW GEMM
-        side_cs = self.side_streams and self.direct
+        side_cs = self.side_streams and self.direct and bias is None
         fork = self._fork() if side_cs else None
         cs_done = None
 
@@ -297,8 +340,10 @@ class ConnectorStep:
             dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
                   ([g["video_connector.linear.weight"]] if self.use_v else [])
             al = ([ga] if self.use_a else []) + ([gv] if self.use_v else [])
-            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, xs, dws, al, dy_row_base=base))
-            if side_cs:
+            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, xs, dws, al, dy_row_base=base, bias=bias))
+            if bias is not None:
+                pass  # db came out of the dW launch
+            elif side_cs:
                 torch.cuda.current_stream().wait_event(self._on_side(fork, "colsum", bias_sums))
             else:
                 self._timed("colsum", bias_sums)
@@ -314,7 +359,9 @@ class ConnectorStep:
         comm = self._comm_stream
         self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw(dy, [xa], [g["audio_connector.linear.weight"]], [ga],
                                                          dy_row_base=base))
-        if side_cs:
+        if bias is not None:   # overlapped NCCL schedule: the bias sums ride on the video-weight launch below
+            pass
+        elif side_cs:
             cs_done = self._on_side(fork, "colsum", bias_sums)
         e1 = torch.cuda.Event()
         e1.record(main)
@@ -323,8 +370,10 @@ class ConnectorStep:
             g.allreduce_span("audio_connector.linear.weight", "audio_connector.linear.weight", prescaled=pre)
         sms = self._num_sms - self.comm_reserve_sms
         self._timed("proj_bwd_dw_v", lambda: L.proj_bwd_dw(dy, [xv], [g["video_connector.linear.weight"]], [gv],
-                                                           dy_row_base=base, max_sms=sms))
-        if cs_done is not None:
+                                                           dy_row_base=base, max_sms=sms, bias=bias))
+        if bias is not None:
+            pass
+        elif cs_done is not None:
             main.wait_event(cs_done)
         else:
             self._timed("colsum", bias_sums)
@@ -338,12 +387,21 @@ class ConnectorStep:
         main.wait_event(e3)
         return g
 
-    def _backward_fused_allreduce(self, dy, base, xa, xv, dba, dbv, ga, gv, cs):
-        """dW GEMM + all-reduce of the whole bucket in ONE launch.  The bias sums run first (on the side stream, under
-        the GEMM) and flag their ranges ready; the GEMM's comm warps reduce them together with the weight tiles."""
+    def _backward_fused_allreduce(self, dy, base, xa, xv, dba, dbv, ga, gv, cs, bias):
+        """dW GEMM + db + all-reduce of the whole bucket in ONE launch: the bias gradients come from the launch's own
+        bias work items, whose epilogue flags them ready; the comm warps reduce them together with the weight tiles.
+        (AVC_BIAS_IN_GEMM=0: the stand-alone bias-sum kernel runs on the side stream under the GEMM and flags them.)"""
         g = self.bucket
         comm = g.peer.next_epoch()
         ex = [t for t in (dba, dbv) if t is not None]
+        if bias is not None:
+            xs = ([xa] if self.use_a else []) + ([xv] if self.use_v else [])
+            dws = ([g["audio_connector.linear.weight"]] if self.use_a else []) + \
+                  ([g["video_connector.linear.weight"]] if self.use_v else [])
+            al = ([ga] if self.use_a else []) + ([gv] if self.use_v else [])
+            self._timed("proj_bwd_dw", lambda: L.proj_bwd_dw_allreduce(dy, xs, dws, al, comm, dy_row_base=base,
+                                                                       bias=bias))
+            return g
 
         def bias_sums():  # one launch; its last CTA flags the sums ready for this epoch
             L.colsum(dy, dba, dbv, self.colsum_ws, alpha0=ga, alpha1=gv, comm=comm, **cs)

@@ -15,8 +15,8 @@ Two ways to reduce the bucket:
 from __future__ import annotations
 
 import os
+import secrets
 import socket
-import tempfile
 import threading
 import time
 from collections import OrderedDict
@@ -26,18 +26,24 @@ import torch
 import torch.distributed as dist
 
 
-def _fd_socket_path(tag: str) -> str:
-    return os.path.join(tempfile.gettempdir(), f"avc_{tag}_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}.sock")
+def _fd_socket_address(tag: str) -> str:
+    """Address of the fd-passing socket.  A leading NUL selects Linux's ABSTRACT socket namespace: no file is created,
+    so nothing can be pre-created, unlinked or left behind in a shared /tmp; `tag` carries a random per-job token
+    (broadcast through the process group) so that a local user cannot squat the name either."""
+    return f"\0avc_{tag}_{os.getuid()}"
 
 
 def _serve_fd(fd: int, nclients: int, tag: str) -> threading.Thread:
-    """Hand a file descriptor to `nclients` local processes over an AF_UNIX socket (SCM_RIGHTS)."""
-    path = _fd_socket_path(tag)
-    if os.path.exists(path):
-        os.unlink(path)
+    """Hand a file descriptor to `nclients` local processes over an AF_UNIX socket (SCM_RIGHTS).  Raises OSError if
+    the socket cannot be bound (the caller turns that into an all-rank fallback)."""
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    srv.bind(path)
-    srv.listen(max(1, nclients))
+    try:
+        srv.bind(_fd_socket_address(tag))
+        srv.listen(max(1, nclients))
+        srv.settimeout(60.0)
+    except OSError:
+        srv.close()
+        raise
 
     def run():
         try:
@@ -45,10 +51,10 @@ def _serve_fd(fd: int, nclients: int, tag: str) -> threading.Thread:
                 conn, _ = srv.accept()
                 socket.send_fds(conn, [b"fd"], [fd])
                 conn.close()
+        except OSError:
+            pass  # a client that never came: the import on that rank fails and every rank falls back together
         finally:
             srv.close()
-            if os.path.exists(path):
-                os.unlink(path)
 
     t = threading.Thread(target=run, daemon=True)
     t.start()
@@ -56,19 +62,22 @@ def _serve_fd(fd: int, nclients: int, tag: str) -> threading.Thread:
 
 
 def _fetch_fd(tag: str, timeout_s: float = 30.0) -> int:
-    path = _fd_socket_path(tag)
+    addr = _fd_socket_address(tag)
     c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
     deadline = time.time() + timeout_s
     while True:
         try:
-            c.connect(path)
+            c.connect(addr)
             break
         except (ConnectionRefusedError, FileNotFoundError):
             if time.time() > deadline:
-                raise TimeoutError(f"no fd server at {path}")
+                c.close()
+                raise TimeoutError(f"no fd server at {addr!r}")
             time.sleep(0.01)
     _, fds, _, _ = socket.recv_fds(c, 16, 1)
     c.close()
+    if not fds:
+        raise OSError("fd server closed the connection without sending a descriptor")
     return fds[0]
 
 
@@ -180,24 +189,32 @@ class PeerMemory:
         if not agree(err is None):
             return None
         handle = None
+        # the socket name carries a random per-job token chosen by rank 0 (nobody can pre-create or guess it)
+        token = [secrets.token_hex(8) if self.rank == 0 else None]
+        if self.world > 1:
+            dist.broadcast_object_list(token, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                                       group=group)
+        tag = f"mc_{token[0]}"
+        server = None
         if self.rank == 0:
             handle, fd = created
-            server = _serve_fd(fd, self.world - 1, "mc")
-            agree(True)                      # the socket is listening
-            server.join(timeout=60)
+            server, err = attempt(lambda: _serve_fd(fd, self.world - 1, tag))
+        listening = agree(err is None)       # the socket is listening (or every rank falls back together)
+        if self.rank == 0:
+            if server is not None and listening:
+                server.join(timeout=60)
             os.close(fd)
-        else:
-            agree(True)
+        elif listening:
 
             def imp():
-                f = _fetch_fd("mc")
+                f = _fetch_fd(tag)
                 try:
                     return L.mc_import(f)
                 finally:
                     os.close(f)
 
             handle, err = attempt(imp)
-        if not agree(err is None):
+        if not listening or not agree(err is None):
             return None
         _, err = attempt(lambda: L.mc_add_device(handle))
         if not agree(err is None):           # every device is in the object before anyone binds memory to it
@@ -341,6 +358,60 @@ class GradBucket:
         for name, p in named_params:
             if name in self.views:
                 p.grad = self.views[name]
+
+
+class FusedGradSync:
+    """Data-parallel gradient sync for the PUBLIC API (`fused_connector(..., grad_sync=...)`,
+    `ClipWhisperModel.enable_data_parallel()`): the four projector parameters' .grad are views of one peer-mapped
+    bucket, the autograd backward writes dW / db straight into them and the dW GEMM launch all-reduces the bucket
+    itself (`avc_proj_bwd_dw_db_allreduce`) -- no NCCL call, no flatten / unflatten copy, and nothing is returned
+    through autograd for those parameters (so gradients are OVERWRITTEN every backward, not accumulated: call the
+    optimizer after every backward, as the reference trainer does, clip_whisper_trainer.py:453-464).
+
+    After `backward()` every rank's `.grad` holds the MEAN over ranks.  Falls back to a plain local bucket + one NCCL
+    all-reduce (`finish()`) when peer mapping is unavailable."""
+
+    NAMES = ("audio_connector.linear.weight", "video_connector.linear.weight", "audio_connector.linear.bias",
+             "video_connector.linear.bias")
+
+    def __init__(self, wa: Optional[torch.Tensor], ba: Optional[torch.Tensor], wv: Optional[torch.Tensor],
+                 bv: Optional[torch.Tensor], process_group=None, multimem: Optional[bool] = None):
+        from . import _lib as L
+
+        params = dict(zip(self.NAMES, (wa, wv, ba, bv)))
+        shapes = {n: tuple(p.shape) for n, p in params.items() if p is not None}
+        dev = next(p for p in params.values() if p is not None).device
+        ddp = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if ddp else 1
+        if multimem is None:
+            multimem = os.environ.get("AVC_COMM_MULTIMEM", "1") == "1"
+        peer = self.world <= L.COMM_MAX_WORLD and (not ddp or dist.get_backend(process_group) == "nccl")
+        try:
+            self.bucket = GradBucket(shapes, dev, process_group=process_group, peer=peer, multimem=multimem and peer)
+        except L.ConnectorError:
+            if not peer:
+                raise
+            self.bucket = GradBucket(shapes, dev, process_group=process_group)
+        self.fused = self.bucket.peer is not None
+        self.bucket.attach([(n, p) for n, p in params.items() if p is not None])
+
+    def views(self, use_a: bool, use_v: bool):
+        g = self.bucket.views
+        return (g.get(self.NAMES[0]) if use_a else None, g.get(self.NAMES[2]) if use_a else None,
+                g.get(self.NAMES[1]) if use_v else None, g.get(self.NAMES[3]) if use_v else None)
+
+    def next_epoch(self):
+        if not self.fused:
+            raise RuntimeError("no peer-mapped bucket: use finish() after backward")
+        return self.bucket.peer.next_epoch()
+
+    def check(self) -> None:
+        if self.fused:
+            self.bucket.peer.check()
+
+    def close(self) -> None:
+        if self.fused:
+            self.bucket.peer.close()
 
 
 def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:

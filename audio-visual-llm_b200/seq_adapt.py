@@ -90,8 +90,8 @@ def adaptive_projection(tensor: torch.Tensor, target_length: int) -> torch.Tenso
         return tensor
     if not tensor.is_cuda:
         raise L.ConnectorError("adaptive_projection: tensor is not on a CUDA device (no CPU fallback)")
-    if tensor.dtype not in (torch.float32, torch.bfloat16):
-        raise L.ConnectorError(f"adaptive_projection: dtype {tensor.dtype} unsupported (fp32 or bf16)")
+    if tensor.dtype not in L.DTYPE_CODES:
+        raise L.ConnectorError(f"adaptive_projection: dtype {tensor.dtype} unsupported (fp32, bf16 or fp16)")
     return _ResampleFn.apply(tensor, target_length)
 
 

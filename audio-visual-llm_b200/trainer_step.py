@@ -78,6 +78,11 @@ class ConnectorAdamW:
             if other_sumsq is not None:
                 clip = clip + other_sumsq.to(clip.device, torch.float32).reshape(1)
         lr = self.lr if lr is None else lr
+        # the kernel updates the parameters through raw pointers, which does not bump torch's version counter: any
+        # cached bf16 pack of the old weights (forward-only fast path of connector_ops.pack_projector) is stale now
+        from .connector_ops import invalidate_pack_cache
+
+        invalidate_pack_cache()
         for n, p in self.params.items():
             dst, alpha = self.packed.get(n, (None, 1.0))
             L.adamw_step(p.data if isinstance(p, torch.nn.Parameter) else p, self._grad(n), self.exp_avg[n],

@@ -8,7 +8,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; nothing is allocated or freed
  *     (except by the avc_comm_alloc / avc_comm_free peer-memory helpers)
- *   - feature / weight / embedding elements are bf16; masks, ids and labels are int64 (reference dtype)
+ *   - GEMM operands (features, packed weights, dY) are bf16; projected rows / inputs_embeds are bf16, fp16 or fp32
+ *     (AVC_DTYPE_*); masks, ids and labels are int64 (reference dtype)
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
  *   - return 0 on success, non-zero on error; avc_last_error() gives the message (thread-local)
  *   - there is no CPU fallback: a device that is not sm_100 is an error
@@ -29,7 +30,14 @@
 extern "C" {
 #endif
 
-#define AVC_ABI_VERSION 2  /* 2: colsum workspace header contract, avc_comm_* / avc_mc_* data-parallel entry points */
+#define AVC_ABI_VERSION 3  /* 2: colsum workspace header contract, avc_comm_* / avc_mc_* data-parallel entry points
+                              3: output dtype codes (fp16), db inside the dW launch (avc_proj_bwd_dw_db*),
+                                 avc_proj_bwd_dx, avc_cast_bf16, avc_gather_bwd */
+
+/* element types of matrices the kernels write (operands of the tensor-core GEMMs are always bf16) */
+#define AVC_DTYPE_BF16 0
+#define AVC_DTYPE_F32 1
+#define AVC_DTYPE_F16 2   /* the reference's use_fp16 mode: fp16 LLM / connector output (clip_whisper_model.py:164) */
 
 enum avc_status {
   AVC_OK = 0,
@@ -89,7 +97,7 @@ AVC_API int avc_gather_fwd(const avc_feat* audio, const avc_feat* video, int32_t
  * Replaces SimpleModalityConnector.forward x2 + weighted sum (modality_connector.py:43-44,
  * clip_whisper_model.py:434) through W = [fs*Wa | (1-fs)*Wv], bias0 = fs*ba, bias1 = (1-fs)*bv. */
 AVC_API int avc_proj_fwd(int32_t nseg, const avc_mat* a /* [nseg] bf16 */, const avc_mat* w /* [nseg] bf16 [N, K_s] */,
-                 const avc_mat* y, int32_t y_is_fp32, const float* bias0, const float* bias1,
+                 const avc_mat* y, int32_t y_dtype /* AVC_DTYPE_* */, const float* bias0, const float* bias1,
                  float bias_scale0, float bias_scale1, const uint8_t* row_flags, int32_t flag_rows0,
                  int32_t flag_rows1, int32_t act /* 0 none, 1 GELU(erf) */, void* stream);
 
@@ -101,6 +109,39 @@ AVC_API int avc_proj_bwd_dw(const avc_mat* dy /* bf16 [b][rows][H] */, int32_t d
                     const avc_mat* x /* [nseg] bf16 */, const avc_mat* dw /* [nseg] fp32 [H, K_s] */,
                     const float* alpha /* [nseg] */, int32_t max_sms /* 0 = all; < SM count leaves SMs free for a
                     concurrent collective (gradient all-reduce overlap) */, void* stream);
+
+/* ---- projector backward: weight AND bias gradients in one launch ------------------------------------------------
+ * avc_proj_bwd_dw plus, from extra 64-wide work items of the same persistent tile schedule (they re-use the dY panels
+ * the weight tiles stream and fill the idle workers of the schedule's last round):
+ *   out_i[h] = alpha_i * sum_{b, r} dY[b, dy_row_base + r, h] * present[b, r, i]          i = 0 (audio), 1 (video)
+ * `present` is a bf16 [batches][rows >= x rows][64] matrix whose column i is 1 where row r of sample b carries a
+ * token of stream i and 0 elsewhere (all ones for dense streams; the zero-padded rows of the shorter stream are what
+ * clip_whisper_model.py:340-345 pads AFTER the projection, so they must not see that stream's bias).  Columns 2..63
+ * are ignored.  Replaces autograd's db = sum dY of nn.Linear (modality_connector.py:32); deterministic. */
+typedef struct avc_bias_grad {
+  const avc_mat* present;  /* bf16 [batches][rows][64] */
+  float* out0;             /* [H] fp32 or NULL */
+  float* out1;             /* [H] fp32 or NULL */
+  float alpha0, alpha1;
+} avc_bias_grad;
+AVC_API int avc_proj_bwd_dw_db(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
+                               const avc_mat* dw, const float* alpha, const avc_bias_grad* bias, int32_t max_sms,
+                               void* stream);
+
+/* ---- projector backward: input gradient (unfrozen towers, freeze_encoders=False: clip_whisper_model.py:1096,1136)
+ * dX[b, r, :] = sum_s dY[b, r, :] . W_s   computed as the forward GEMM with B = W_s^T from avc_pack_weight_t
+ * (w_t[s]: bf16 [K_in, H_s]); dx is bf16 / fp16 / fp32 (dx_dtype = AVC_DTYPE_*). */
+AVC_API int avc_proj_bwd_dx(const avc_mat* dy /* [nseg] bf16 */, int32_t nseg, const avc_mat* w_t /* [nseg] */,
+                            const avc_mat* dx, int32_t dx_dtype, void* stream);
+
+/* ---- gather backward: input gradients of the align / stack / concat step ------------------------------------------
+ * d_feat[b, t, :] = sum over the tokens j that read frame t (j / repeat == t / stack, j < tokens of sample b) of
+ *                   dA[tok_offset[b] + j, col_off + (t % stack) * dim : + dim],   zero for frames no token reads
+ * (frames at or past valid_frames[b], or past the token cap).  `feat` describes the OUTPUT d_feat here (ptr, strides,
+ * frames, dim, stack, repeat, valid_frames as in avc_gather_fwd); out_dtype = AVC_DTYPE_BF16 or AVC_DTYPE_F32. */
+AVC_API int avc_gather_bwd(const void* da /* bf16 [total_rows, a_row_stride] */, int64_t a_row_stride, int64_t col_off,
+                           const avc_feat* feat, int32_t out_dtype, int32_t batch, const int32_t* tok_offset,
+                           int32_t tokens_per_sample, void* stream);
 
 /* ---- data parallel: the same weight-gradient GEMM with the gradient all-reduce fused into it ------------------
  * One process per GPU; every rank keeps its projector gradients in ONE flat fp32 bucket allocated with
@@ -144,6 +185,11 @@ AVC_API int avc_proj_bwd_dw_allreduce(const avc_mat* dy, int32_t dy_row_base, in
                                       const avc_mat* dw, const float* alpha, const avc_comm* comm,
                                       const float* extra0, int64_t extra0_len, const float* extra1,
                                       int64_t extra1_len, int32_t max_sms, void* stream);
+/* The same with the bias gradients produced by the launch itself (avc_proj_bwd_dw_db): bias->out0 / out1 are the
+ * extra ranges (inside the local bucket), flagged ready by the epilogue of the last bias work item. */
+AVC_API int avc_proj_bwd_dw_db_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
+                                         const avc_mat* dw, const float* alpha, const avc_bias_grad* bias,
+                                         const avc_comm* comm, int32_t max_sms, void* stream);
 /* Enqueue after the kernel that wrote this rank's extra ranges (same stream): flags them ready for comm->epoch. */
 AVC_API int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extra1_len, void* stream);
 
@@ -192,6 +238,10 @@ AVC_API int avc_colsum_comm(const avc_mat* dy /* bf16 */, int32_t dy_row_base, i
 /* ---- weight pack: W_bf16 = bf16(alpha * W_fp32) (folds fusion_scale into the projector) -------- */
 AVC_API int avc_pack_weight(const float* src, int64_t src_ld, void* dst_bf16, int64_t dst_ld, int64_t rows,
                     int64_t cols, float alpha, void* stream);
+/* ---- operand cast: dst_bf16[r, c] = bf16(alpha * src[r, c]) for src of type AVC_DTYPE_* (the base class's cast of the
+ * connector input to the module dtype, modality_connector.py:18-19; also fp16 / fp32 dY -> the bf16 GEMM operand). */
+AVC_API int avc_cast_bf16(const void* src, int32_t src_dtype, int64_t src_ld, void* dst_bf16, int64_t dst_ld,
+                          int64_t rows, int64_t cols, float alpha, void* stream);
 
 /* ---- splice: scatter projected rows + text embeddings into inputs_embeds, emit masks ------------
  * inputs_embeds[b, p] = Y[tok_offset[b] + rank(p)]  where input_ids[b, p] == placeholder_id
@@ -217,7 +267,7 @@ typedef struct avc_splice {
   int32_t label_mode;
   const int64_t* labels_in;   /* [batch, label_len] or NULL */
   int32_t label_len;
-  int32_t elem_size;          /* bytes per element of y / embed_table / inputs_embeds: 2 (bf16) or 4 (fp32); 0 = 2 */
+  int32_t elem_size;          /* bytes per element of y / embed_table / inputs_embeds: 2 (bf16, fp16) or 4 (fp32); 0 = 2 */
   int64_t* labels_out;        /* [batch, seq] or NULL */
   int32_t* status;            /* device int32 or NULL */
   int32_t av_rows_in_place;   /* fwd: 1 = the placeholder rows of inputs_embeds were already written by
@@ -235,8 +285,8 @@ AVC_API int avc_splice_bwd(const avc_splice* s, const void* d_inputs_embeds, voi
  * With the CSR matrix of adaptive average pooling (windows [floor(i*S/L), ceil((i+1)*S/L)), weight 1/len) or
  * of linear interpolation with align_corners (two taps) this replaces _adaptive_projection
  * (clip_whisper_model.py:621-676); with the transposed matrix it is that op's backward.
- * elem_size: 2 = bf16, 4 = fp32 (accumulation is fp32 either way). */
-AVC_API int avc_row_resample(const void* x, void* out, int32_t elem_size, int32_t batch, int32_t src_rows,
+ * dtype: AVC_DTYPE_* of x and out (accumulation is fp32 either way). */
+AVC_API int avc_row_resample(const void* x, void* out, int32_t dtype, int32_t batch, int32_t src_rows,
                              int32_t dst_rows, int32_t hidden, const int32_t* row_ptr, const int32_t* col_idx,
                              const float* weight, void* stream);
 

@@ -28,22 +28,26 @@ class FakeEvent:
 class FakeEngine:
     fused, mc = False, None
 
-    def __init__(self, shape, plan, dev, seed=0, fuse_gather=True, fused_allreduce=None):
-        self.shape, self.direct, self.overlap_comm = shape, fuse_gather, False
+    def __init__(self, shape, plan, dev, seed=0, fuse_gather=True, fused_allreduce=None, ragged_range=None):
+        self.shape, self.direct, self.overlap_comm = shape, fuse_gather and ragged_range is None, False
         self.fused_allreduce = FakeEngine.fused and fused_allreduce is not False
+        self.ragged = ragged_range is not None
         self.fused_tokens = self.M = shape.batch * 375
         self.S = 391
+        self.K = 6144
+        self.bias_in_gemm = True
         self.status = torch.zeros(1, dtype=torch.int32)
-        peer = types.SimpleNamespace(mc=FakeEngine.mc, check=lambda: None) if self.fused_allreduce else None
+        peer = types.SimpleNamespace(mc=FakeEngine.mc, check=lambda: None, close=lambda: None) \
+            if self.fused_allreduce else None
         self.bucket = types.SimpleNamespace(peer=peer)
-        self.launches_per_step = 6 if fuse_gather else 8
+        self.launches_per_step = 5 if self.direct else 7
         self.events = None
 
     def step(self, allreduce=True):
         pass
 
     def enable_kernel_timing(self):
-        names = ["proj_fwd", "splice_fwd", "proj_bwd_dw", "colsum"] + ([] if self.direct else ["gather", "splice_bwd"])
+        names = ["proj_fwd", "splice_fwd", "proj_bwd_dw"] + ([] if self.direct else ["gather", "splice_bwd"])
         self.events = {n: [(FakeEvent(), FakeEvent())] for n in names}
 
     def gemm_flops(self):
@@ -69,8 +73,13 @@ def run_bench(argv, world, fused, mc):
 
     env = {"RANK": "0", "WORLD_SIZE": str(world), "LOCAL_RANK": "0"}
     fake_e2e = {"value": 1.0, "unit": bench.UNIT, "h2d_bytes_per_step": 1, "d2h_bytes_per_step": 1}
+    fake_check = {"ok": True, "output_max_rel": 1e-3, "dw_max_rel": 1e-5}
+    fake_eager = {"ms_per_step": 200.0, "value": 1.0, "unit": bench.UNIT, "best": "two_linear",
+                  "cublas": {"fwd_ms": 90.0, "dw_ms": 95.0}}
     with mock.patch.dict("os.environ", env), mock.patch.object(sys, "argv", ["bench.py"] + argv), \
             mock.patch.object(E, "ConnectorStep", FakeEngine), mock.patch("torch.cuda.set_device"), \
+            mock.patch.object(bench, "self_check", lambda *a, **k: dict(fake_check)), \
+            mock.patch.object(bench, "gpu_eager_leg", lambda *a, **k: dict(fake_eager, cublas=dict(fake_eager["cublas"]))), \
             mock.patch("torch.cuda.Event", FakeEvent), mock.patch("torch.cuda.synchronize"), \
             mock.patch("torch.cuda.empty_cache"), mock.patch("torch.device", lambda *a: "cpu"), \
             mock.patch.object(bench, "run_e2e", lambda *a, **k: dict(fake_e2e)), \
@@ -87,7 +96,8 @@ def run_bench(argv, world, fused, mc):
 
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-             "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"}
+             "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches",
+             "sustained", "self_check", "gpu_eager", "strong_scaling"}
 
 
 @pytest.mark.parametrize("argv,world,fused,mc,scaling,collective", [
@@ -105,7 +115,12 @@ def test_bench_line(avc, argv, world, fused, mc, scaling, collective):
     assert collective in d["config"]["collective"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert d["roofline"]["bound"] == "tensor" and d["roofline"]["unit"] == "TFLOP/s"
-    assert d["gpu_launches"] == 6 * 5
+    assert d["gpu_launches"] == 5 * 5
+    assert d["self_check"]["ok"] is True
+    assert {"steps", "ms_per_step", "value", "clocks", "roofline"} <= set(d["sustained"])
+    assert d["gpu_eager"]["ours_over_eager_step"] > 0 and set(d["gpu_eager"]["ours_over_cublas"]) == {"fwd", "dw"}
+    if world > 1 and scaling == "weak":
+        assert d["strong_scaling"]["global_batch"] == 256 and d["strong_scaling"]["batch_per_gpu"] == 256 // world
     if world == 1:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
@@ -114,3 +129,12 @@ def test_bench_line(avc, argv, world, fused, mc, scaling, collective):
         assert len(d["per_rank_kernel_ms"]["proj_bwd_dw_ms"]) == world
     if scaling == "strong":
         assert d["config"]["batch_per_gpu"] == 256 // world and d["config"]["global_batch"] == 256
+
+
+@pytest.mark.parametrize("config", ["cfg1", "cfg3", "cfg4"])
+def test_bench_line_other_configs(avc, config):
+    d = run_bench(["--steps", "5", "--warmup", "3", "--config", config, "--no-cpu-baseline"], 1, False, None)
+    assert BASE_KEYS <= set(d)
+    assert d["config"]["workload"].startswith(config + ":")
+    if config == "cfg4":
+        assert "gather" in d["kernels"] and "splice_bwd" in d["kernels"], "ragged config: stand-alone kernels on the path"

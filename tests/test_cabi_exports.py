@@ -18,7 +18,9 @@ def declared_symbols():
 def test_header_declares_the_path_entry_points():
     syms = declared_symbols()
     for need in ("avc_gather_fwd", "avc_proj_fwd", "avc_proj_bwd_dw", "avc_colsum", "avc_splice_fwd",
-                 "avc_splice_bwd", "avc_pack_weight", "avc_row_resample", "avc_device_check", "avc_last_error"):
+                 "avc_splice_bwd", "avc_pack_weight", "avc_row_resample", "avc_device_check", "avc_last_error",
+                 "avc_proj_bwd_dw_db", "avc_proj_bwd_dw_db_allreduce", "avc_proj_bwd_dx", "avc_gather_bwd",
+                 "avc_cast_bf16"):
         assert need in syms
 
 
@@ -76,7 +78,7 @@ def test_plain_c_program_links_against_the_abi(avc, tmp_path):
     src.write_text(
         '#include "avconnector_b200.h"\n#include <stdio.h>\n'
         "int main(void) {\n"
-        "  avc_feat f; avc_mat m; avc_splice s; (void)f; (void)m; (void)s;\n"
+        "  avc_feat f; avc_mat m; avc_splice s; avc_bias_grad bg; (void)f; (void)m; (void)s; (void)bg;\n"
         '  printf("abi=%d ws=%zu\\n", avc_abi_version(), avc_colsum_workspace_bytes(4096));\n'
         "  int rc = avc_device_check(0);\n"
         '  printf("device_check=%d msg=%s\\n", rc, avc_last_error());\n'
@@ -87,4 +89,4 @@ def test_plain_c_program_links_against_the_abi(avc, tmp_path):
                         "-L", str(lib_dir), "-lavconnector_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0 and "abi=2" in out.stdout and "device_check=" in out.stdout
+    assert out.returncode == 0 and "abi=3" in out.stdout and "device_check=" in out.stdout

@@ -5,7 +5,9 @@ Instead of a full oracle run, size-independent properties are checked on the B20
   * index work is re-derived with vectorised integer arithmetic on the CPU and must match bit-exactly
     (attention mask, labels, placeholder -> row map);
   * round trip: splice-bwd(splice-fwd(Y)) returns Y bit-exactly (scatter then gather is the identity);
-  * bilinear probe: u^T dW v == sum_r (dY u)_r (X v)_r and db == column sums, both recomputed in fp64;
+  * sampled dW entries: the four corners of EVERY 512 x 256 output tile of the dW GEMM plus 64 x 64 random (h, k) pairs
+    per stream, recomputed in fp64 from the same bf16 operands (a dropped or misplaced tile cannot hide), a bilinear
+    probe u^T dW v over the whole matrix, and db == column sums in fp64;
   * linearity of the gradient in the upstream gradient: dW(g1 + g2) == dW(g1) + dW(g2) up to fp32 rounding.
 Tolerances: max-rel <= 1e-2 / cosine >= 0.9999 for bf16 outputs (north_star), 1e-3 for fp32 gradient probes.
 """
@@ -27,6 +29,24 @@ def cos(got, ref):
 
 def gpu_randn(gen, *shape, scale=1.0):
     return (torch.randn(*shape, generator=gen, device="cuda") * scale)
+
+
+def check_dw_entries(dw, dY, X, scale, seed, tile_m=512, tile_n=256, nrand=64, tol=1e-3):
+    """dw [H, K] fp32 vs scale * dY[B, N, H]^T X[B, N, K] (fp64) on every tile's corners and nrand x nrand random entries."""
+    H, K = dw.shape
+    g = torch.Generator().manual_seed(seed)
+    hs = sorted({h for t in range(0, H, tile_m) for h in (t, min(t + tile_m, H) - 1)} |
+                set(torch.randperm(H, generator=g)[:nrand].tolist()))
+    ks = sorted({k for t in range(0, K, tile_n) for k in (t, min(t + tile_n, K) - 1)} |
+                set(torch.randperm(K, generator=g)[:nrand].tolist()))
+    hs_t, ks_t = torch.tensor(hs, device=dw.device), torch.tensor(ks, device=dw.device)
+    M = dY.shape[0] * dY.shape[1]
+    ref = scale * (dY[:, :, hs_t].reshape(M, -1).t() @ X[:, :, ks_t].reshape(M, -1))
+    got = dw[hs_t][:, ks_t].double()
+    rms = float(ref.pow(2).mean().sqrt())
+    err = float(((got - ref).abs() / (ref.abs() + rms)).max())
+    assert err <= tol, f"dW sampled entries: max relative error {err:.3e} over {len(hs)} x {len(ks)} entries"
+    return len(hs) * len(ks)
 
 
 def stacked_rows(x, k, b, j):
@@ -122,6 +142,7 @@ def test_full_size_uniform_layout(avc, cuda_dev, name):
         vv = torch.randn(Ka, generator=torch.Generator().manual_seed(3), dtype=torch.float64).cuda()
         probe = sa * (dyu * (Xa @ vv)).sum()
         assert abs(float(u @ wa.grad.double() @ vv) - float(probe)) <= 1e-3 * float((dyu.abs() * (Xa @ vv).abs()).sum()) * sa
+        assert check_dw_entries(wa.grad, dY, Xa, sa, 5) >= 4096
         dba = sa * (dY * (rows * c["ka"] < c["Ta"]).view(1, N, 1)).sum((0, 1))
         assert rel(ba.grad, dba) <= 1e-4
         del Xa
@@ -132,6 +153,7 @@ def test_full_size_uniform_layout(avc, cuda_dev, name):
         vv = torch.randn(Kv, generator=torch.Generator().manual_seed(4), dtype=torch.float64).cuda()
         probe = sv * (dyu * (Xv @ vv)).sum()
         assert abs(float(u @ wv.grad.double() @ vv) - float(probe)) <= 1e-3 * float((dyu.abs() * (Xv @ vv).abs()).sum()) * sv
+        assert check_dw_entries(wv.grad, dY, Xv, sv, 6) >= 4096
         dbv = sv * (dY * (rows * c["kv"] < c["Tv"]).view(1, N, 1)).sum((0, 1))
         assert rel(bv.grad, dbv) <= 1e-4
         del Xv

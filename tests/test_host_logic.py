@@ -154,24 +154,32 @@ def test_fd_passing_between_threads(tmp_path, monkeypatch):
     `parallel._serve_fd` / `_fetch_fd`.  Checked here with an ordinary file: the received descriptor is a NEW number
     that refers to the same open file."""
     import os
-    import tempfile
+    import secrets
 
     from audio_visual_llm_b200 import parallel
 
-    monkeypatch.setenv("MASTER_PORT", str(40000 + os.getpid() % 20000))
-    monkeypatch.setattr(tempfile, "tempdir", str(tmp_path))
+    tag = "test_" + secrets.token_hex(8)  # random per-job token, as _setup_multicast broadcasts it
+    assert parallel._fd_socket_address(tag).startswith("\0"), "abstract namespace: no file in a shared /tmp"
     payload = tmp_path / "payload.bin"
     payload.write_bytes(b"multicast-object")
     fd = os.open(payload, os.O_RDONLY)
     try:
-        server = parallel._serve_fd(fd, 2, "test")
-        got = [parallel._fetch_fd("test", timeout_s=5.0) for _ in range(2)]
+        server = parallel._serve_fd(fd, 2, tag)
+        got = [parallel._fetch_fd(tag, timeout_s=5.0) for _ in range(2)]
         server.join(timeout=5)
         assert not server.is_alive()
         for g in got:
             assert g != fd
             assert os.pread(g, 64, 0) == b"multicast-object"
             os.close(g)
-        assert not os.path.exists(parallel._fd_socket_path("test")), "the server removes its socket"
+        # a second server on the same name fails loudly (rank 0 turns that into an all-rank fallback) ...
+        s2 = parallel._serve_fd(fd, 1, tag + "x")
+        with pytest.raises(OSError):
+            parallel._serve_fd(fd, 1, tag + "x")
+        os.close(parallel._fetch_fd(tag + "x", timeout_s=5.0))
+        s2.join(timeout=5)
+        # ... and a client without a server times out instead of hanging
+        with pytest.raises(TimeoutError):
+            parallel._fetch_fd(tag + "_nobody", timeout_s=0.2)
     finally:
         os.close(fd)

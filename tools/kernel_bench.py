@@ -112,6 +112,10 @@ def main():
     report("splice_fwd", lambda: L.splice_fwd(sp, Y, emb), nbytes=2 * B * S * H * 2 + 16 * B * S)
     report("splice_bwd", lambda: L.splice_bwd(sp, d_emb, dY), nbytes=2 * M * H * 2)
     report("proj_bwd_dw", lambda: L.proj_bwd_dw(dY, [A], [dW], [1.0]), flops=2 * M * K * H)
+    present = L.present_operand(1, M, dev)
+    db1 = torch.empty(H, dtype=torch.float32, device=dev)
+    report("proj_bwd_dw_db", lambda: L.proj_bwd_dw(dY, [A], [dW], [1.0], bias=(present, db, db1, 1.0, 1.0)),
+           flops=2 * M * K * H)
     # same FLOPs / tile grid as the dW GEMM, but K-major operands (TN mode): isolates the cost of the MN-major path
     At = torch.randn(H, M, device=dev).to(torch.bfloat16)
     Wt = torch.randn(K, M, device=dev).to(torch.bfloat16)
