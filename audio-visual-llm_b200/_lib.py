@@ -25,6 +25,7 @@ EXPORTS = (
     "avc_mc_supported", "avc_mc_padded_bytes", "avc_mc_create", "avc_mc_import", "avc_mc_add_device",
     "avc_mc_bucket_alloc", "avc_mc_bucket_free",
     "avc_proj_bwd_dw_db", "avc_proj_bwd_dw_db_allreduce", "avc_proj_bwd_dx", "avc_gather_bwd", "avc_cast_bf16",
+    "avc_debug_gemm_profile",
 )
 
 # AVC_DTYPE_* codes of include/avconnector_b200.h
@@ -347,6 +348,11 @@ def mc_bucket_alloc(handle: int, padded_bytes: int) -> AvcMcBucket:
 
 def mc_bucket_free(b: AvcMcBucket) -> None:
     check(load().avc_mc_bucket_free(C.byref(b)))
+
+
+def debug_gemm_profile(buf: Optional[torch.Tensor]) -> None:
+    """Per-CTA cycle counters of the next projector GEMM launches into `buf` (int64 [148, 8], zeroed); None: off."""
+    check(load().avc_debug_gemm_profile(C.c_void_p(_ptr(buf))))
 
 
 def comm_flag_bytes() -> int:

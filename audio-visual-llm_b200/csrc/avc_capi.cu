@@ -453,6 +453,11 @@ int avc_comm_signal_extra(const avc_comm* comm, int64_t extra0_len, int64_t extr
   return AVC_OK;
 }
 
+int avc_debug_gemm_profile(void* device_buf) {
+  avc::set_gemm_profile_buffer(static_cast<unsigned long long*>(device_buf));
+  return AVC_OK;
+}
+
 size_t avc_comm_flag_bytes(void) { return static_cast<size_t>(avc::COMM_FLAG_WORDS) * 4; }
 
 int avc_comm_alloc(size_t bytes, void** ptr) {

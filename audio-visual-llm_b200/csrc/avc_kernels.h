@@ -102,7 +102,11 @@ struct GemmArgs {
   float* bias_out[2];        // [d_rows] fp32 each, may be null
   float bias_alpha[2];
   CommArgs comm;             // NT only: world >= 1 fuses the gradient all-reduce into the launch (0: plain GEMM)
+  // optional per-CTA cycle counters (debug, avc_debug_gemm_profile): [cta][8] = {producer wait-empty, MMA wait-full,
+  // MMA wait-tempty, epilogue wait-tfull, epilogue body, tiles, kernel cycles, 0}
+  unsigned long long* prof;
 };
+void set_gemm_profile_buffer(unsigned long long* buf);
 
 // N tile that minimises (waves x per-tile time) for `m_blocks` x ceil(n_s / bn) tiles on `num_sms` persistent CTAs.
 int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_workers);

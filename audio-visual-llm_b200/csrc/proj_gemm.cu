@@ -175,7 +175,10 @@ __device__ __forceinline__ void comm_reduce(const CommArgs& cm, int64_t base, in
   else comm_reduce_rows<COMM_MAX_WORLD, true>(cm, base, ld, rows, nvec, lane);
 }
 
-template <int MODE, int OUT, int CG, int MT, int COMM>
+// ACT (forward only): 0 = identity, 1 = erf GELU in the epilogue.  A template parameter, not a run-time branch: ptxas
+// if-converts the branch, and ~1600 predicated-off GELU instructions per 64-column chunk then sit in every epilogue
+// warp's instruction stream (measured: the epilogue of a 512 x 256 tile took 12 us instead of 3).
+template <int MODE, int OUT, int CG, int MT, int COMM, int ACT = 0>
 __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const __grid_constant__ GemmArgs args) {
   using C = Cfg<CG, MT>;
   constexpr bool OUT_F32 = OUT == GEMM_OUT_F32;
@@ -288,56 +291,84 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     // ======================================================================= TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t pol) {
-        if (CG == 2) tma_load_3d_cg2(dst, m, bar & kPeerBitMask, c0, c1, c2, pol);
-        else tma_load_3d_hint(dst, m, bar, c0, c1, c2, pol);
-      };
       // forward: activations stream through once per N sweep, the weights are re-read by every M block
       const uint64_t pol_a = args.l2_hints ? (MODE == GEMM_TN ? kEvictFirst : kEvictNormal) : kEvictNormal;
       const uint64_t pol_b = args.l2_hints ? (MODE == GEMM_TN ? kEvictLast : kEvictNormal) : kEvictNormal;
-      for (int w = worker; w < all_work; w += num_workers) {
+      // Operand panels of one work item (what does not change along its K loop)
+      struct Item {
+        int w;
+        int c1a, c2a;        // TN: A row / batch coordinate.   NT: first M column of this CTA (c1a)
+        int c1b;             // TN: B (weight) row.              NT: first N column of this CTA
+        const CUtensorMap* mapb;
+        int nbx;             // NT: 64-wide B atoms to load
+        uint32_t tx;         // bytes this CTA's loads deliver per stage
+      };
+      auto locate = [&](Item& t, int w) {
         int m_blk, n_blk, n_off, width;
         const bool bias = decode(w, m_blk, n_blk, n_off, width);
         const int w_cta = width / CG;  // B rows / columns of this CTA that the MMA reads
+        t.w = w;
+        t.tx = cta_tx;
         if (MODE == GEMM_TN) {
-          const int b = m_blk / args.m_tiles_per_batch;
-          const int r0 = (m_blk % args.m_tiles_per_batch) * TILE_M + static_cast<int>(rank) * (BM * MT);
-          const int n0 = n_blk * bn + n_off + static_cast<int>(rank) * w_cta;
-          for (int seg = 0; seg < args.nseg; ++seg) {
-            for (int kb = 0; kb < args.seg_kblocks[seg]; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              if (leader) mbar_arrive_expect_tx(full_bar(stage), cta_tx * CG);
-              const uint32_t sa = smem_base + stage * STAGE_BYTES;
-              load(sa, &args.ma[seg], full_bar(stage), kb * BK, r0, b, pol_a);
-              load(sa + A_BYTES, &args.mb[seg], full_bar(stage), kb * BK, n0, 0, pol_b);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            }
-          }
+          t.c2a = m_blk / args.m_tiles_per_batch;
+          t.c1a = (m_blk % args.m_tiles_per_batch) * TILE_M + static_cast<int>(rank) * (BM * MT);
+          t.c1b = n_blk * bn + n_off + static_cast<int>(rank) * w_cta;
+          t.mapb = nullptr;
+          t.nbx = 1;
         } else {
-          const int m0 = m_blk * TILE_M + static_cast<int>(rank) * (BM * MT);
           const int seg = (!bias && n_blk >= args.n_blocks_seg0) ? 1 : 0;
-          const int nl0 = bias ? static_cast<int>(rank) * w_cta
-                               : (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off + static_cast<int>(rank) * w_cta;
+          t.c1a = m_blk * TILE_M + static_cast<int>(rank) * (BM * MT);
+          t.c2a = 0;
+          t.c1b = bias ? static_cast<int>(rank) * w_cta
+                       : (n_blk - (seg ? args.n_blocks_seg0 : 0)) * bn + n_off + static_cast<int>(rank) * w_cta;
           // bias item: the B operand is one 64-wide atom of F (columns past GEMM_BIAS_COLS are zero-filled by TMA)
-          const CUtensorMap* mapb = bias ? &args.mf : &args.mb[seg];
-          const int nbx = bias ? 1 : nb_boxes;
-          const uint32_t tx = bias ? (A_BYTES + MN_ATOM_BYTES) : cta_tx;
-          for (int bb = 0; bb < args.red_batches; ++bb) {
-            for (int kb = 0; kb < args.red_kblocks_per_batch; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              if (leader) mbar_arrive_expect_tx(full_bar(stage), tx * CG);
-              const uint32_t sa = smem_base + stage * STAGE_BYTES;
-              const int row = kb * BK;
-#pragma unroll
-              for (int i = 0; i < BM * MT / 64; ++i)
-                load(sa + i * MN_ATOM_BYTES, &args.ma[0], full_bar(stage), m0 + i * 64, args.a_row_base + row, bb,
-                     pol_a);
-              for (int i = 0; i < nbx; ++i)
-                load(sa + A_BYTES + i * MN_ATOM_BYTES, mapb, full_bar(stage), nl0 + i * 64, row, bb, pol_b);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            }
-          }
+          t.mapb = bias ? &args.mf : &args.mb[seg];
+          t.nbx = bias ? 1 : nb_boxes;
+          if (bias) t.tx = A_BYTES + MN_ATOM_BYTES;
         }
+      };
+      // visits the TMA boxes of K iteration `it` of item t: f(map, smem offset inside the stage, c0, c1, c2, policy)
+      auto boxes = [&](const Item& t, int it, auto&& f) {
+        if (MODE == GEMM_TN) {
+          const int seg = it < args.seg_kblocks[0] ? 0 : 1;
+          const int kb = it - (seg ? args.seg_kblocks[0] : 0);
+          f(&args.ma[seg], 0u, kb * BK, t.c1a, t.c2a, pol_a);
+          f(&args.mb[seg], static_cast<uint32_t>(A_BYTES), kb * BK, t.c1b, 0, pol_b);
+        } else {
+          const int bb = it / args.red_kblocks_per_batch;
+          const int row = (it - bb * args.red_kblocks_per_batch) * BK;
+#pragma unroll
+          for (int i = 0; i < BM * MT / 64; ++i)
+            f(&args.ma[0], static_cast<uint32_t>(i * MN_ATOM_BYTES), t.c1a + i * 64, args.a_row_base + row, bb, pol_a);
+          for (int i = 0; i < t.nbx; ++i)
+            f(t.mapb, static_cast<uint32_t>(A_BYTES + i * MN_ATOM_BYTES), t.c1b + i * 64, row, bb, pol_b);
+        }
+      };
+      // (An L2 prefetch cursor running a few K iterations ahead of the loads -- cp.async.bulk.prefetch.tensor, by every
+      // CTA or only by the first CTA of a round that touches a panel -- measured 15 - 40 % SLOWER: the prefetches occupy
+      // the TMA unit like loads do.  profiles/README.md, round 2.)
+      Item cur;
+      long long t_wait = 0;
+      const long long t_begin = clock64();
+      for (int w = worker; w < all_work; w += num_workers) {
+        locate(cur, w);
+        for (int it = 0; it < total_kb; ++it) {
+          const long long t0 = clock64();
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          t_wait += clock64() - t0;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), cur.tx * CG);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t bar = full_bar(stage);
+          boxes(cur, it, [&](const CUtensorMap* m, uint32_t off, int c0, int c1, int c2, uint64_t pol) {
+            if (CG == 2) tma_load_3d_cg2(sa + off, m, bar & kPeerBitMask, c0, c1, c2, pol);
+            else tma_load_3d_hint(sa + off, m, bar, c0, c1, c2, pol);
+          });
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (args.prof != nullptr) {
+        args.prof[blockIdx.x * 8 + 0] = static_cast<unsigned long long>(t_wait);
+        args.prof[blockIdx.x * 8 + 6] = static_cast<unsigned long long>(clock64() - t_begin);
       }
     }
     __syncwarp();
@@ -345,14 +376,19 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     // ======================================================================= MMA issuer (leader CTA only)
     if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      long long t_full = 0, t_tempty = 0;
       for (int w = worker; w < all_work; w += num_workers) {
         int m_blk, n_blk, n_off, width;
         decode(w, m_blk, n_blk, n_off, width);
         const uint32_t idesc = make_idesc_bf16(BM * CG, width, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
+        const long long t0 = clock64();
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        t_tempty += clock64() - t0;
         tc_fence_after();
         for (int it = 0; it < total_kb; ++it) {
+          const long long t1 = clock64();
           mbar_wait(full_bar(stage), phase);
+          t_full += clock64() - t1;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
@@ -390,6 +426,10 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
         else umma_commit(tfull_bar(acc));
         if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
       }
+      if (args.prof != nullptr) {
+        args.prof[blockIdx.x * 8 + 1] = static_cast<unsigned long long>(t_full);
+        args.prof[blockIdx.x * 8 + 2] = static_cast<unsigned long long>(t_tempty);
+      }
     }
     __syncwarp();
   } else if (COMM == 0 || warp < 2 + EPI_WARPS) {
@@ -398,6 +438,8 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     const int ew = warp - 2;   // staging buffer owner index
     constexpr int COLS = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
     uint32_t acc = 0, acc_phase = 0, buf = 0;
+    long long t_tfull = 0, t_body = 0, n_tiles = 0;
+    long long t_ph[5] = {0, 0, 0, 0, 0};  // per chunk: wait staging buffer, TMEM load, math + st.shared, proxy fence, TMA store
     for (int w = worker; w < all_work; w += num_workers) {
       int m_blk, n_blk, n_off, width;
       const bool bias = decode(w, m_blk, n_blk, n_off, width);
@@ -416,8 +458,29 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       const float alpha = args.alpha[seg];
       const int ncols = args.d_cols[seg];
 
+      // Bias slice of this item's columns, spread over the lanes (float4 group G = column / 4 lives in lane G % 32, slot
+      // G / 32) and loaded BEFORE the wait for the accumulator: the L2 latency of these loads (~800 cycles under load,
+      // paid twice per 64-column chunk when they sat inside the chunk loop) disappears behind the main loop.
+      float4 bias_reg[2][2];
+      if (MODE == GEMM_TN) {
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const float* bp = s2 == 0 ? args.bias0 : args.bias1;
+#pragma unroll
+          for (int slot = 0; slot < 2; ++slot) {
+            const int n = out_col0 + (slot * 32 + lane) * 4;
+            bias_reg[s2][slot] = (bp != nullptr && (slot * 32 + lane) * 4 < width && n < ncols)
+                                     ? __ldg(reinterpret_cast<const float4*>(bp + n))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      const long long te0 = clock64();
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      const long long te1 = clock64();
+      t_tfull += te1 - te0;
+      ++n_tiles;
 
 #pragma unroll 1
       for (int h = 0; h < MT; ++h) {  // MT = 2: accumulator h holds rows [128 h, 128 h + 128) of this CTA
@@ -435,9 +498,9 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           f0 = my_row < args.flag_rows0 ? args.bias_scale[0] : 0.f;
           f1 = my_row < args.flag_rows1 ? args.bias_scale[1] : 0.f;
         }
-        if (args.bias0 == nullptr) f0 = 0.f;
-        if (args.bias1 == nullptr) f1 = 0.f;
       }
+      const bool has_b0 = MODE == GEMM_TN && args.bias0 != nullptr;
+      const bool has_b1 = MODE == GEMM_TN && args.bias1 != nullptr;
       const uint32_t t_row = tmem_base + (MT == 2 ? h * BN : acc * BN) + (static_cast<uint32_t>(q * 32) << 16);
       if (MODE == GEMM_NT && bias) {
         // bias item: accumulator column i of this thread's row h is sum_r dY[r, h] * F[r, i]
@@ -454,8 +517,11 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       for (int c = 0; c < nchunk; ++c) {
         const int col = out_col0 + c * COLS;
         // the store issued from this staging buffer two chunks ago must have finished reading it
+        const long long tc0 = clock64();
         if (lane == 0 || (MODE == GEMM_TN && args.scatter_rows > 0)) bulk_wait_read<1>();
         __syncwarp();
+        const long long tc1 = clock64();
+        t_ph[0] += tc1 - tc0;
         const uint32_t sbuf = s_epi + (ew * 2 + buf) * EPI_BUF_BYTES;
         const uint32_t srow = sbuf + lane * 128;
         // COLS accumulator columns of this thread's row -> registers
@@ -469,34 +535,40 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           }
           tmem_ld_wait();
         }
+        const long long tc2 = clock64();
+        t_ph[1] += tc2 - tc1;
         float x[COLS];
 #pragma unroll
-        for (int g = 0; g < COLS / 4; ++g) {
-          float* xg = &x[4 * g];
+        for (int i = 0; i < COLS; ++i) x[i] = __uint_as_float(v[i]);
+        if (MODE == GEMM_TN) {
+          // Bias: x += f0 * bias0[n] + f1 * bias1[n] with the per-row multipliers f0 / f1 (0 on rows whose token lacks
+          // that stream, so no per-lane branches: every predicate below is warp-uniform).  The bias values come from the
+          // lane-distributed copy loaded at the top of the work item (columns past N hold zeros).
+          constexpr int GPC = COLS / 4;  // float4 groups per chunk
 #pragma unroll
-          for (int e = 0; e < 4; ++e) xg[e] = __uint_as_float(v[4 * g + e]);
-          if (MODE == GEMM_TN) {
-            const int n = col + 4 * g;
-            if (n < ncols) {
-              if (f0 != 0.f) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias0 + n));
-                xg[0] = fmaf(f0, b.x, xg[0]); xg[1] = fmaf(f0, b.y, xg[1]);
-                xg[2] = fmaf(f0, b.z, xg[2]); xg[3] = fmaf(f0, b.w, xg[3]);
-              }
-              if (f1 != 0.f) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias1 + n));
-                xg[0] = fmaf(f1, b.x, xg[0]); xg[1] = fmaf(f1, b.y, xg[1]);
-                xg[2] = fmaf(f1, b.z, xg[2]); xg[3] = fmaf(f1, b.w, xg[3]);
-              }
+          for (int s2 = 0; s2 < 2; ++s2) {
+            if (s2 == 0 ? !has_b0 : !has_b1) continue;  // warp-uniform
+            const float f = s2 == 0 ? f0 : f1;
+            const int slot = (c * GPC) >> 5;             // warp-uniform: the chunk's groups share one slot
+            const float4 mine = slot == 0 ? bias_reg[s2][0] : bias_reg[s2][1];
+            const int lane0 = (c * GPC) & 31;
+#pragma unroll
+            for (int g = 0; g < GPC; ++g) {
+              const float bx = __shfl_sync(0xffffffffu, mine.x, lane0 + g);
+              const float by = __shfl_sync(0xffffffffu, mine.y, lane0 + g);
+              const float bz = __shfl_sync(0xffffffffu, mine.z, lane0 + g);
+              const float bw = __shfl_sync(0xffffffffu, mine.w, lane0 + g);
+              x[4 * g + 0] = fmaf(f, bx, x[4 * g + 0]); x[4 * g + 1] = fmaf(f, by, x[4 * g + 1]);
+              x[4 * g + 2] = fmaf(f, bz, x[4 * g + 2]); x[4 * g + 3] = fmaf(f, bw, x[4 * g + 3]);
             }
-            if (args.act == 1) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) xg[e] = gelu_erf(xg[e]);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) xg[e] *= alpha;
           }
+          if (ACT == 1) {
+#pragma unroll
+            for (int i = 0; i < COLS; ++i) x[i] = gelu_erf(x[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < COLS; ++i) x[i] *= alpha;
         }
         // one 128-byte staging row per thread, 16-byte chunks XOR-swizzled (matches SWIZZLE_128B)
 #pragma unroll
@@ -515,8 +587,12 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
                            pack_bf16x2(x[o + 4], x[o + 5]), pack_bf16x2(x[o + 6], x[o + 7]));
           }
         }
+        const long long tc3 = clock64();
+        t_ph[2] += tc3 - tc2;
         fence_proxy_async_smem();
         __syncwarp();
+        const long long tc4 = clock64();
+        t_ph[3] += tc4 - tc3;
         if (MODE == GEMM_TN && args.scatter_rows > 0) {
           // packed rows m = b * scatter_rows + j go to row j of batch entry b of the output map (the AV region of
           // inputs_embeds).  A 32-row box inside one sample is one TMA store (rows past the last sample's end are
@@ -539,6 +615,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           bulk_commit();
         }
         buf ^= 1u;
+        t_ph[4] += clock64() - tc4;
       }
       }  // h
       // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the issuer
@@ -549,6 +626,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
+      t_body += clock64() - te1;
       if (COMM != 0 && bias) {
         // The bias gradients of this rank are complete once every epilogue warp of every bias item has stored its
         // rows (plain stores): the last of them flags the extra ranges ready at every rank that owns a chunk of them.
@@ -586,6 +664,12 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     }
     if (lane == 0 || (MODE == GEMM_TN && args.scatter_rows > 0)) bulk_wait_all<0>();
     __syncwarp();
+    if (args.prof != nullptr && warp == 2 && lane == 0) {
+      args.prof[blockIdx.x * 8 + 3] = static_cast<unsigned long long>(t_tfull);
+      args.prof[blockIdx.x * 8 + 4] = static_cast<unsigned long long>(t_body);
+      args.prof[blockIdx.x * 8 + 5] = static_cast<unsigned long long>(n_tiles);
+      for (int i = 0; i < 5; ++i) args.prof[148 * 8 + blockIdx.x * 8 + i] = static_cast<unsigned long long>(t_ph[i]);
+    }
   } else if (COMM != 0) {
     // ======================================================================= comm warps (fused gradient all-reduce)
     const CommArgs& cm = args.comm;
@@ -668,6 +752,8 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
   }
 }
 
+unsigned long long* g_prof = nullptr;
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e != nullptr ? atoi(e) : dflt;
@@ -713,6 +799,7 @@ int plan_schedule(GemmArgs& args, GemmMode mode, int num_sms) {
 template <int CG, int MT>
 cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, GemmOut out, int num_sms, cudaStream_t stream) {
   GemmArgs args = args_in;
+  args.prof = g_prof;
   const int workers = plan_schedule<CG>(args, mode, num_sms);
   const bool comm = args.comm.world > 0;
   const bool out_fp32 = out == GEMM_OUT_F32;
@@ -751,6 +838,11 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, GemmOut out, int n
     }
   }
   if (mode == GEMM_TN) {
+    if (args.act == 1) {
+      if (out == GEMM_OUT_F32) return run(gemm_kernel<GEMM_TN, GEMM_OUT_F32, CG, MT, 0, 1>);
+      if (out == GEMM_OUT_F16) return run(gemm_kernel<GEMM_TN, GEMM_OUT_F16, CG, MT, 0, 1>);
+      return run(gemm_kernel<GEMM_TN, GEMM_OUT_BF16, CG, MT, 0, 1>);
+    }
     if (out == GEMM_OUT_F32) return run(gemm_kernel<GEMM_TN, GEMM_OUT_F32, CG, MT, 0>);
     if (out == GEMM_OUT_F16) return run(gemm_kernel<GEMM_TN, GEMM_OUT_F16, CG, MT, 0>);
     return run(gemm_kernel<GEMM_TN, GEMM_OUT_BF16, CG, MT, 0>);
@@ -768,6 +860,8 @@ __global__ void comm_signal_extra_kernel(const __grid_constant__ CommArgs cm) {
 }
 
 }  // namespace
+
+void set_gemm_profile_buffer(unsigned long long* buf) { g_prof = buf; }
 
 int gemm_cta_group() {
   const int v = env_int("AVC_GEMM_CTA_GROUP", 2);

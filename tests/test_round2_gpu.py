@@ -325,7 +325,8 @@ def test_splice_bulk_rows_across_piece_boundaries(avc, cuda_dev, H, dtype):
     for b, c in enumerate(counts):
         pos = torch.randperm(S, generator=g)[:c].sort().values
         ids[b, pos] = PH
-    ids[0, 3] = 777           # out-of-range id: zero row
+    free = (ids[0] != PH).nonzero().flatten()
+    ids[0, int(free[3])] = 777  # out-of-range id at a text position: zero row
     offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32)
     M = int(offs[-1])
     y = torch.randn(M, H, generator=g).to(dtype)
@@ -457,6 +458,7 @@ def test_freeze_flags_and_unfrozen_tower_gradients(avc, cuda_dev):
     assert gw is not None and float(gw.abs().max()) > 0, "the connector's dX reaches the unfrozen tower"
     # reference on the CPU: same tower, same connector, same LLM head, fp32
     import copy
+    m.llm.seen = None  # a non-leaf tensor cannot be deep-copied
     tower, llm = copy.deepcopy(m.whisper).cpu().float(), copy.deepcopy(m.llm).cpu().float()
     for p in tower.parameters():
         p.grad = None
