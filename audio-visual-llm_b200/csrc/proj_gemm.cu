@@ -142,6 +142,7 @@ __device__ __forceinline__ void comm_reduce_rows(const CommArgs& cm, int64_t bas
 // (1 + 1 / world) x the bucket instead of 2 (world - 1) / world x with peer loads and stores.
 __device__ __forceinline__ void comm_reduce_rows_mc(const CommArgs& cm, int64_t base, int ld, int rows, int nvec,
                                                     int lane) {
+  // 8 vectors (4 KB per warp) in flight.  16 measured no faster at 2 GPUs (the registers it costs slow the GEMM part).
   constexpr int C = 8;
   const int total = rows * nvec;
   for (int v0 = 0; v0 < total; v0 += 32 * C) {
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
   const int worker = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int num_workers = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
+  if (args.prof != nullptr && threadIdx.x == 0) args.prof[2 * 148 * 8 + blockIdx.x * 8 + 0] = globaltimer_ns();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.ma[0]);
     tma_prefetch_desc(&args.mb[0]);
@@ -429,6 +431,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       if (args.prof != nullptr) {
         args.prof[blockIdx.x * 8 + 1] = static_cast<unsigned long long>(t_full);
         args.prof[blockIdx.x * 8 + 2] = static_cast<unsigned long long>(t_tempty);
+        args.prof[2 * 148 * 8 + blockIdx.x * 8 + 5] = globaltimer_ns();
       }
     }
     __syncwarp();
@@ -669,6 +672,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       args.prof[blockIdx.x * 8 + 4] = static_cast<unsigned long long>(t_body);
       args.prof[blockIdx.x * 8 + 5] = static_cast<unsigned long long>(n_tiles);
       for (int i = 0; i < 5; ++i) args.prof[148 * 8 + blockIdx.x * 8 + i] = static_cast<unsigned long long>(t_ph[i]);
+      args.prof[2 * 148 * 8 + blockIdx.x * 8 + 1] = globaltimer_ns();
     }
   } else if (COMM != 0) {
     // ======================================================================= comm warps (fused gradient all-reduce)
@@ -679,6 +683,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     constexpr int RG = TILE_M / COMM_UNIT_ROWS;  // row groups (units) per work item
     bool ok = true;
     int cur = -1;
+    const bool stamp = args.prof != nullptr && warp == 2 + EPI_WARPS && lane == 0;
     // The schedule's rounds (num_workers items each) complete one after the other, the items of one round together.
     // Per round, the units of the items this rank owns are dealt to the GPU's comm warps in CONTIGUOUS runs, so a warp
     // waits for (and pays the system-scope acquire of) one or two items per round instead of one per unit.
@@ -696,6 +701,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           ok = comm_wait(lf + COMM_ITEM_FLAGS + w * COMM_MAX_WORLD, cm, lane);
           cur = w;
           if (!ok) break;
+          if (stamp && r1 == total_work) args.prof[2 * 148 * 8 + blockIdx.x * 8 + 2] = globaltimer_ns();
         }
         int m_blk, n_blk, n_off, width;
         decode(w, m_blk, n_blk, n_off, width);
@@ -729,9 +735,11 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     // This rank is done once all its comm warps are; the last one tells every rank and then waits until every rank
     // has finished writing into this rank's bucket -- the launch does not complete before the bucket is final.
     __syncwarp();
+    if (stamp) args.prof[2 * 148 * 8 + blockIdx.x * 8 + 3] = globaltimer_ns();
     int last = 0;
     if (lane == 0) {
       __threadfence_system();
+      if (stamp) args.prof[2 * 148 * 8 + blockIdx.x * 8 + 6] = globaltimer_ns();
       if (atomicAdd(lf + COMM_DONE_COUNT, 1u) == static_cast<uint32_t>(G - 1)) {
         atomicExch(lf + COMM_DONE_COUNT, 0u);
         __threadfence_system();
@@ -740,10 +748,12 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       }
     }
     if (__shfl_sync(0xffffffffu, last, 0)) comm_wait(lf + COMM_DONE_FLAGS, cm, lane);
+    if (stamp) args.prof[2 * 148 * 8 + blockIdx.x * 8 + 4] = globaltimer_ns();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (args.prof != nullptr && threadIdx.x == 0) args.prof[2 * 148 * 8 + blockIdx.x * 8 + 7] = globaltimer_ns();
   if (CG == 2) cluster_sync_all();  // the peer may still signal this CTA's barriers / read its smem until here
   if (warp == 1) {
     tc_fence_after();

@@ -529,6 +529,7 @@ def main():
         scaling = "strong"
     eng, plan, shape = make_engine(pkg, w, dev, 1234 + rank)
     eng.overlap_comm = bool(args.overlap) or eng.overlap_comm
+    multicast = eng.bucket.peer is not None and eng.bucket.peer.mc is not None  # (the bucket is closed further down)
 
     # ------------------------------------------------------------------ device-resident throughput (`value`)
     sampler = ClockSampler(local_rank)
@@ -675,7 +676,7 @@ def main():
     if world == 1:
         collective = "none"
     elif eng.fused_allreduce:
-        mc = eng.bucket.peer is not None and eng.bucket.peer.mc is not None
+        mc = multicast
         collective = ("projector-grad all-reduce fused into the dW GEMM launch (100.7 MB fp32 flat bucket; comm warps of "
                       "the GEMM CTAs reduce finished tiles over NVLink while later tiles are computed; transport: " +
                       ("NVSwitch multicast mapping, multimem.ld_reduce + multimem.st)" if mc

@@ -101,10 +101,11 @@ AVC_API int avc_proj_fwd(int32_t nseg, const avc_mat* a /* [nseg] bf16 */, const
                  float bias_scale0, float bias_scale1, const uint8_t* row_flags, int32_t flag_rows0,
                  int32_t flag_rows1, int32_t act /* 0 none, 1 GELU(erf) */, void* stream);
 
-/* Debug / profiling hook: when `device_buf` (2 x 148 x 8 uint64, zero it first) is non-NULL every later projector GEMM
+/* Debug / profiling hook: when `device_buf` (3 x 148 x 8 uint64, zero it first) is non-NULL every later projector GEMM
  * launch records per-CTA SM-cycle counters into it: [cta][0] producer waiting for a free smem stage, [1] MMA issuer
  * waiting for operands, [2] MMA issuer waiting for a free accumulator, [3] first epilogue warp waiting for a full
- * accumulator, [4] its epilogue time, [5] its work items, [6] producer loop cycles.  NULL switches it off. */
+ * accumulator, [4] its epilogue time, [5] its work items, [6] producer loop cycles; the second block holds the epilogue's
+ * per-phase cycles, the third %globaltimer stamps (kernel start, epilogue / comm-warp milestones, end).  NULL: off. */
 AVC_API int avc_debug_gemm_profile(void* device_buf);
 
 /* ---- projector backward: weight gradient ------------------------------------------------------

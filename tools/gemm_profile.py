@@ -22,7 +22,7 @@ bias = torch.randn(H, device=dev)
 Y = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
 dY = torch.randn(M, H, device=dev).to(torch.bfloat16)
 dW = torch.empty(H, K, dtype=torch.float32, device=dev)
-prof = torch.zeros(2 * 148, 8, dtype=torch.int64, device=dev)
+prof = torch.zeros(3 * 148, 8, dtype=torch.int64, device=dev)
 
 
 def run(name, fn, iters=20):
@@ -42,7 +42,7 @@ def run(name, fn, iters=20):
     torch.cuda.synchronize()
     L.debug_gemm_profile(None)
     pall = prof.cpu().double()
-    p, ph = pall[:148], pall[148:]
+    p, ph = pall[:148], pall[148:296]
     lead = p[0::2]   # even CTAs lead their pair (MMA issuer counters live there)
     tiles = p[:, 5].clamp_min(1)
     rec = {"kernel": name, "ms": round(ms, 4), "kcycles_kernel(producer loop)": round(float(p[:, 6].mean()) / 1e3, 1),
