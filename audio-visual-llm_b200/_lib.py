@@ -25,7 +25,7 @@ EXPORTS = (
     "avc_mc_supported", "avc_mc_padded_bytes", "avc_mc_create", "avc_mc_import", "avc_mc_add_device",
     "avc_mc_bucket_alloc", "avc_mc_bucket_free",
     "avc_proj_bwd_dw_db", "avc_proj_bwd_dw_db_allreduce", "avc_proj_bwd_dx", "avc_gather_bwd", "avc_cast_bf16",
-    "avc_debug_gemm_profile",
+    "avc_debug_gemm_profile", "avc_proj_bwd_dw_plan",
 )
 
 # AVC_DTYPE_* codes of include/avconnector_b200.h
@@ -226,19 +226,56 @@ def _bias_grad(present: torch.Tensor, out0: Optional[torch.Tensor], out1: Option
     return b
 
 
+_DW_PLAN: dict = {}
+_DW_WORKSPACE: dict = {}
+
+
+def dw_plan(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], with_bias: bool):
+    """(reduction slices, workspace bytes) the dW launch would use for these operands (`avc_proj_bwd_dw_plan`)."""
+    import os
+
+    key = (tuple(dy.shape), tuple(tuple(x.shape) for x in x_segs), bool(with_bias), dy.device,
+           os.environ.get("AVC_GEMM_KSPLIT"), os.environ.get("AVC_GEMM_MAX_WORKERS"))
+    hit = _DW_PLAN.get(key)
+    if hit is None:
+        splits, nbytes = C.c_int32(1), C.c_size_t(0)
+        check(load().avc_proj_bwd_dw_plan(C.byref(mat(dy)), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
+                                          C.c_int32(1 if with_bias else 0), C.byref(splits), C.byref(nbytes)))
+        hit = (int(splits.value), int(nbytes.value))
+        if len(_DW_PLAN) > 64:
+            _DW_PLAN.clear()
+        _DW_PLAN[key] = hit
+    return hit
+
+
+def dw_workspace(device, nbytes: int) -> Optional[torch.Tensor]:
+    """Per-device scratch of the split-reduction dW launch: zero-filled when (re)allocated, the launches leave its
+    arrival counters zero.  Calls that share it must be ordered on one stream (they are: the autograd backward)."""
+    if nbytes <= 0:
+        return None
+    device = torch.device(device)
+    ws = _DW_WORKSPACE.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _DW_WORKSPACE[device] = ws
+    return ws
+
+
 def proj_bwd_dw(dy: torch.Tensor, x_segs: Sequence[torch.Tensor], dw_segs: Sequence[torch.Tensor],
-                alpha: Sequence[float], dy_row_base: int = 0, max_sms: int = 0, bias=None) -> None:
-    """bias = (present, db0, db1, alpha0, alpha1): also produce the bias gradients inside the same launch."""
+                alpha: Sequence[float], dy_row_base: int = 0, max_sms: int = 0, bias=None,
+                workspace: Optional[torch.Tensor] = None, split: bool = True) -> None:
+    """bias = (present, db0, db1, alpha0, alpha1): also produce the bias gradients inside the same launch.
+    With few output tiles the launch splits the row reduction over the idle CTA pairs (`split`; scratch from
+    `dw_workspace` unless `workspace` is given)."""
     al = (C.c_float * len(x_segs))(*alpha)
-    if bias is None:
-        check(load().avc_proj_bwd_dw(
-            C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
-            _mat_array([mat(t) for t in dw_segs]), al, C.c_int32(max_sms), stream_ptr()))
-        return
-    bg = _bias_grad(*bias)
+    if workspace is None and split and max_sms == 0:
+        workspace = dw_workspace(dy.device, dw_plan(dy, x_segs, bias is not None)[1])
+    bg = _bias_grad(*bias) if bias is not None else None
     check(load().avc_proj_bwd_dw_db(
         C.byref(mat(dy)), C.c_int32(dy_row_base), C.c_int32(len(x_segs)), _mat_array([mat(t) for t in x_segs]),
-        _mat_array([mat(t) for t in dw_segs]), al, C.byref(bg), C.c_int32(max_sms), stream_ptr()))
+        _mat_array([mat(t) for t in dw_segs]), al, C.byref(bg) if bg is not None else None,
+        C.c_void_p(_ptr(workspace)), C.c_size_t(0 if workspace is None else workspace.numel() * workspace.element_size()),
+        C.c_int32(max_sms), stream_ptr()))
 
 
 def proj_bwd_dx(dy_segs: Sequence[torch.Tensor], wt_segs: Sequence[torch.Tensor], dx: torch.Tensor) -> None:

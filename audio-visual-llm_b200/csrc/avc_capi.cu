@@ -315,9 +315,26 @@ static int fill_comm(const avc_comm* c, const float* extra0, int64_t extra0_len,
   return AVC_OK;
 }
 
+// Byte layout of the split-reduction workspace for S slices: [arrival counters][partial bias sums][partial dW tiles]
+struct SplitLayout {
+  size_t counters, bias, tiles, total;
+};
+static SplitLayout split_layout(int base_items, int64_t H, int64_t ktot, int splits) {
+  SplitLayout l;
+  // the arrival counters live in a FIXED 64 KB header: a workspace re-used by launches of other shapes must never have
+  // partial sums written where a later launch expects zeroed counters (split launches have < 148 base items)
+  (void)base_items;
+  l.counters = 65536;
+  l.bias = (static_cast<size_t>(splits) * 2 * H * sizeof(float) + 255) & ~static_cast<size_t>(255);
+  l.tiles = static_cast<size_t>(splits) * H * ktot * sizeof(float);
+  l.total = l.counters + l.bias + l.tiles;
+  return l;
+}
+
 static int proj_bwd_dw_impl(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
                             const float* alpha, const avc_bias_grad* bias, const avc::CommArgs* comm,
-                            uint64_t bucket_bytes, int32_t max_sms, void* stream) {
+                            uint64_t bucket_bytes, int32_t max_sms, void* stream, void* workspace = nullptr,
+                            size_t workspace_bytes = 0, int32_t* plan_splits = nullptr, size_t* plan_bytes = nullptr) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   if (max_sms < 0) return fail(AVC_ERR_INVALID, "proj_bwd_dw: negative max_sms");
@@ -383,6 +400,45 @@ static int proj_bwd_dw_impl(const avc_mat* dy, int32_t dy_row_base, int32_t nseg
     g.bias_alpha[0] = bias->alpha0;
     g.bias_alpha[1] = bias->alpha1;
   }
+  // few tiles: slices of the reduction fill the idle workers (needs a workspace; not together with the fused all-reduce)
+  {
+    int64_t ktot = 0;
+    for (int s = 0; s < nseg; ++s) ktot += x[s].cols;
+    const int base_items = g.num_m_blocks * g.num_n_blocks + g.bias_items;
+    const int total_kb = g.red_batches * g.red_kblocks_per_batch;
+    int splits = comm == nullptr ? avc::gemm_dw_splits(base_items, di.num_sms / cg, total_kb) : 1;
+    if (plan_splits != nullptr) {  // planning call: report and return
+      *plan_splits = splits;
+      if (plan_bytes != nullptr) *plan_bytes = splits > 1 ? split_layout(base_items, H, ktot, splits).total : 0;
+      return AVC_OK;
+    }
+    if (workspace == nullptr) splits = 1;
+    while (splits > 1 && split_layout(base_items, H, ktot, splits).total > workspace_bytes) --splits;
+    if (splits > 1) {
+      if (reinterpret_cast<uintptr_t>(workspace) & 255)
+        return fail(AVC_ERR_INVALID, "proj_bwd_dw: the split-reduction workspace must be 256-byte aligned");
+      const SplitLayout l = split_layout(base_items, H, ktot, splits);
+      uint8_t* wsp = static_cast<uint8_t*>(workspace);
+      g.ksplit = splits;
+      g.split_count = reinterpret_cast<uint32_t*>(wsp);
+      g.ws_bias = reinterpret_cast<float*>(wsp + l.counters);
+      g.ws = reinterpret_cast<float*>(wsp + l.counters + l.bias);
+      g.ws_split_stride = H * ktot;
+      g.ws_ld = static_cast<int>(ktot);
+      int64_t col = 0;
+      for (int s = 0; s < nseg; ++s) {
+        g.ws_seg_col[s] = static_cast<int>(col);
+        if (int rc = make_map3d(&g.mws[s], g.ws + col, 1, x[s].cols, H, splits, ktot, H * ktot, 32, 32,
+                                "proj_bwd_dw split workspace"))
+          return rc;
+        g.d_ptr[s] = static_cast<float*>(dw[s].ptr);
+        g.d_ld[s] = dw[s].row_stride;
+        if (reinterpret_cast<uintptr_t>(dw[s].ptr) & 15 || dw[s].row_stride % 4 != 0)
+          return fail(AVC_ERR_INVALID, "proj_bwd_dw: dW must be 16-byte aligned with a row stride that is a multiple of 4");
+        col += x[s].cols;
+      }
+    }
+  }
   if (comm != nullptr) {
     if (cg != 2) return fail(AVC_ERR_UNSUPPORTED, "proj_bwd_dw_allreduce needs the CTA-pair GEMM (AVC_GEMM_CTA_GROUP=2)");
     g.comm = *comm;
@@ -412,9 +468,29 @@ int avc_proj_bwd_dw(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const 
 }
 
 int avc_proj_bwd_dw_db(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x, const avc_mat* dw,
-                       const float* alpha, const avc_bias_grad* bias, int32_t max_sms, void* stream) {
-  if (bias == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_db: null bias descriptor");
-  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, bias, nullptr, 0, max_sms, stream);
+                       const float* alpha, const avc_bias_grad* bias, void* workspace, size_t workspace_bytes,
+                       int32_t max_sms, void* stream) {
+  return proj_bwd_dw_impl(dy, dy_row_base, nseg, x, dw, alpha, bias, nullptr, 0, max_sms, stream, workspace,
+                          workspace_bytes);
+}
+
+int avc_proj_bwd_dw_plan(const avc_mat* dy, int32_t nseg, const avc_mat* x, int32_t with_bias, int32_t* splits,
+                         size_t* workspace_bytes) {
+  if (splits == nullptr || workspace_bytes == nullptr) return fail(AVC_ERR_INVALID, "proj_bwd_dw_plan: null output");
+  if (dy == nullptr || x == nullptr || nseg < 1 || nseg > 2) return fail(AVC_ERR_INVALID, "proj_bwd_dw_plan: bad operands");
+  // the planner only looks at extents: stand-in output descriptors / bias descriptor with the right shapes
+  avc_mat dw[2];
+  for (int s = 0; s < nseg; ++s) {
+    dw[s].ptr = x[s].ptr;  // never dereferenced by the planning path
+    dw[s].rows = dy->cols; dw[s].cols = x[s].cols; dw[s].row_stride = x[s].cols; dw[s].batches = 1; dw[s].batch_stride = 0;
+  }
+  avc_mat f = *dy;
+  f.cols = avc::GEMM_BIAS_COLS; f.row_stride = avc::GEMM_BIAS_COLS; f.rows = x[0].rows;
+  f.batch_stride = f.rows * f.row_stride;
+  float dummy = 0.f;
+  avc_bias_grad b = {&f, &dummy, nullptr, 1.f, 1.f};
+  return proj_bwd_dw_impl(dy, 0, nseg, x, dw, nullptr, with_bias ? &b : nullptr, nullptr, 0, 0, nullptr, nullptr, 0,
+                          splits, workspace_bytes);
 }
 
 int avc_proj_bwd_dw_db_allreduce(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,

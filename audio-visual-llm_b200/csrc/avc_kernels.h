@@ -101,6 +101,20 @@ struct GemmArgs {
   int bias_items;
   float* bias_out[2];        // [d_rows] fp32 each, may be null
   float bias_alpha[2];
+  // NT, few tiles: split the reduction of every work item into ksplit slices (see gemm_dw_splits).  Partial tiles go to
+  // the workspace ws = [ksplit][d_rows][ws_ld] fp32 through mws[seg] ([ksplit][d_rows][d_cols[seg]] at column
+  // ws_seg_col[seg]); partial bias sums to ws_bias = [ksplit][2][d_rows]; split_count = zeroed, self-resetting arrival
+  // counters [(tiles + bias items)][8].  The final sums are written through d_ptr / d_ld (the dW segments).
+  int ksplit;
+  CUtensorMap mws[2];
+  float* ws;
+  int64_t ws_split_stride;   // elements between two slices of the workspace
+  int ws_ld;                 // row pitch of the workspace (elements)
+  int ws_seg_col[2];
+  float* ws_bias;
+  uint32_t* split_count;
+  float* d_ptr[2];
+  int64_t d_ld[2];
   CommArgs comm;             // NT only: world >= 1 fuses the gradient all-reduce into the launch (0: plain GEMM)
   // optional per-CTA cycle counters (debug, avc_debug_gemm_profile): [cta][8] = {producer wait-empty, MMA wait-full,
   // MMA wait-tempty, epilogue wait-tfull, epilogue body, tiles, kernel cycles, 0}
@@ -119,6 +133,10 @@ int gemm_m_subtiles(int cta_group, GemmMode mode);
 // m_subtiles * GEMM_BM rows of A and bn / cta_group rows of B
 cudaError_t launch_gemm(const GemmArgs& args, GemmMode mode, GemmOut out, int cta_group, int m_subtiles,
                         int num_sms, cudaStream_t stream);
+// Reduction slices per work item that minimise the dW launch's makespan for `base_items` (tiles + bias items) on
+// `workers` persistent workers with `total_kb` K iterations each: ceil(items * S / workers) / S + a per-slice overhead,
+// S <= 8, at least 8 K iterations per slice.  1 when the items already fill the workers.
+int gemm_dw_splits(int base_items, int workers, int total_kb);
 // work items (tiles + tail sub-tiles) the launch above will schedule; the fused all-reduce needs <= COMM_MAX_ITEMS
 int gemm_work_items(const GemmArgs& args, int cta_group, int num_sms);
 // flags every owner that this rank's extra ranges (bias gradients) hold their partial sums for `epoch`

@@ -27,6 +27,7 @@ struct Item {
   int nzero;    // frames to zero-fill
   int mod;
 };
+constexpr int G_MAX_STAGE_BYTES = 8192;  // a stack wider than this is moved in chunks of whole frames
 
 __device__ __forceinline__ void locate_row(const GatherArgs& a, int64_t m, int& b, int& j) {
   if (a.tok_offset == nullptr) {
@@ -53,9 +54,11 @@ __device__ __forceinline__ int valid_len(const GatherArgs& a, int mod, int b) {
   return len;
 }
 
+// An item = one chunk of one stream's stack of one token: `fpc[mod]` consecutive frames (the whole stack when it fits
+// in a stage, i.e. nch[mod] == 1).  Items of a row are numbered [audio chunks | video chunks].
 __global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_constant__ GatherArgs a, int nmods,
                                                                int mod0, int stage_bytes,
-                                                               int zero_bytes) {
+                                                               int zero_bytes, int fpc0, int fpc1, int nch0, int nch1) {
   extern __shared__ __align__(128) uint8_t g_smem[];
   // layout: [zero block][warp rings][barriers]
   const uint32_t s_zero = smem_u32(g_smem);
@@ -74,7 +77,8 @@ __global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_const
   __syncthreads();
 
   if (lane == 0) {
-    const int64_t total_items = a.total_rows * nmods;
+    const int per_row = nch0 + nch1;
+    const int64_t total_items = a.total_rows * per_row;
     const int64_t gwarps = static_cast<int64_t>(gridDim.x) * G_WARPS;
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * G_WARPS + warp;
     const int64_t my_items = gw < total_items ? (total_items - gw + gwarps - 1) / gwarps : 0;
@@ -83,20 +87,25 @@ __global__ void __launch_bounds__(G_WARPS * 32) gather_kernel(const __grid_const
     auto make_item = [&](int64_t n) {
       Item it;
       const int64_t id = gw + n * gwarps;
-      const int64_t m = id / nmods;
-      it.mod = (nmods == 2) ? static_cast<int>(id - m * 2) : mod0;
+      const int64_t m = id / per_row;
+      const int sub = static_cast<int>(id - m * per_row);
+      it.mod = sub < nch0 ? 0 : 1;
+      const int chunk = sub < nch0 ? sub : sub - nch0;
       int b, j;
       locate_row(a, m, b, j);
       const int mod = it.mod;
+      const int fpc = mod == 0 ? fpc0 : fpc1;
       const int len = valid_len(a, mod, b);
-      const int64_t f0 = static_cast<int64_t>(j / a.rep[mod]) * a.k[mod];
+      const int c0 = chunk * fpc;                                   // first frame of the chunk inside the stack
+      const int cf = a.k[mod] - c0 < fpc ? a.k[mod] - c0 : fpc;     // frames in this chunk
+      const int64_t f0 = static_cast<int64_t>(j / a.rep[mod]) * a.k[mod] + c0;
       int64_t nv = len - f0;
-      nv = nv < 0 ? 0 : (nv > a.k[mod] ? a.k[mod] : nv);
+      nv = nv < 0 ? 0 : (nv > cf ? cf : nv);
       it.nvalid = static_cast<int>(nv);
-      it.nzero = a.k[mod] - it.nvalid;
+      it.nzero = cf - it.nvalid;
       it.src = a.src[mod] + b * a.batch_stride[mod] + f0 * a.frame_stride[mod];
-      it.dst = a.dst + m * a.dst_row_bytes + (mod == 1 ? seg1_off : 0);
-      if (a.row_flags != nullptr && (nmods == 1 || mod == 0)) {
+      it.dst = a.dst + m * a.dst_row_bytes + (mod == 1 ? seg1_off : 0) + static_cast<int64_t>(c0) * a.frame_bytes[mod];
+      if (a.row_flags != nullptr && chunk == 0 && (nmods == 1 || mod == 0)) {
         uint8_t fl = 0;
         if (a.src[0] != nullptr) {
           const int la = (mod == 0) ? len : valid_len(a, 0, b);
@@ -174,12 +183,19 @@ cudaError_t launch_gather(const GatherArgs& a, int num_sms, cudaStream_t stream)
   if (nmods == 0) return cudaErrorInvalidValue;
   const int mod0 = a.src[0] != nullptr ? 0 : 1;
   int stage_bytes = 0, zero_bytes = 16;
+  int fpc[2] = {1, 1}, nch[2] = {0, 0};
   for (int i = 0; i < 2; ++i) {
     if (a.src[i] == nullptr) continue;
     if (a.frame_bytes[i] % 16 != 0 || a.frame_stride[i] % 16 != 0 || a.batch_stride[i] % 16 != 0 ||
         (reinterpret_cast<uintptr_t>(a.src[i]) & 15) != 0)
       return cudaErrorMisalignedAddress;
-    const int seg = a.k[i] * a.frame_bytes[i];
+    // whole stack per item when it fits in a stage, else chunks of whole frames (a frame wider than a stage is its
+    // own chunk: the per-CTA shared-memory check below then decides)
+    fpc[i] = a.k[i] * a.frame_bytes[i] <= G_MAX_STAGE_BYTES ? a.k[i]
+                                                            : (G_MAX_STAGE_BYTES / a.frame_bytes[i] > 0
+                                                                   ? G_MAX_STAGE_BYTES / a.frame_bytes[i] : 1);
+    nch[i] = (a.k[i] + fpc[i] - 1) / fpc[i];
+    const int seg = fpc[i] * a.frame_bytes[i];
     stage_bytes = seg > stage_bytes ? seg : stage_bytes;
     zero_bytes = a.frame_bytes[i] > zero_bytes ? a.frame_bytes[i] : zero_bytes;
   }
@@ -195,12 +211,12 @@ cudaError_t launch_gather(const GatherArgs& a, int num_sms, cudaStream_t stream)
   if (e != cudaSuccess) return e;
   int ctas_per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
-  const int64_t total_items = a.total_rows * nmods;
+  const int64_t total_items = a.total_rows * (nch[0] + nch[1]);
   int64_t grid = static_cast<int64_t>(num_sms) * ctas_per_sm;
   const int64_t need = (total_items + G_WARPS - 1) / G_WARPS;
   if (grid > need) grid = need;
-  gather_kernel<<<static_cast<int>(grid), G_WARPS * 32, smem, stream>>>(a, nmods, mod0, stage_bytes,
-                                                                         zero_bytes);
+  gather_kernel<<<static_cast<int>(grid), G_WARPS * 32, smem, stream>>>(a, nmods, mod0, stage_bytes, zero_bytes, fpc[0],
+                                                                         fpc[1], nch[0], nch[1]);
   return cudaGetLastError();
 }
 

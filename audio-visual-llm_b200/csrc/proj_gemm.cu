@@ -252,8 +252,14 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
   // dW only: after the tiles, one GEMM_BIAS_COLS-wide "bias item" per M block contracts the same dY panel with the
   // token-present operand F instead of X -> columns 0 / 1 of its accumulator are the bias gradients of that M block.
   // They are the shortest items of the list and sit at its end, where the last (partial) round has idle workers.
-  const int all_work = total_work + (MODE == GEMM_NT ? args.bias_items : 0);
-  // returns true for a bias item
+  // dW with few tiles (fewer than workers): every item is cut into `ksplit` slices of the reduction (K iterations
+  // [s * total_kb / ksplit, (s + 1) * total_kb / ksplit)); the slices of an item are neighbours in the work list, their
+  // partial results go to a workspace and the LAST epilogue warp to arrive per 32-row slab adds them in slice order
+  // (deterministic) into the real output.  ksplit == 1 everywhere else.
+  const int ksplit = MODE == GEMM_NT ? args.ksplit : 1;
+  const int base_work = total_work + (MODE == GEMM_NT ? args.bias_items : 0);
+  const int all_work = base_work * ksplit;
+  // returns true for a bias item; w is a BASE item index (work item / ksplit)
   auto decode = [&](int w, int& m_blk, int& n_blk, int& n_off, int& width) -> bool {
     int tile = w;
     n_off = 0;
@@ -353,8 +359,10 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       long long t_wait = 0;
       const long long t_begin = clock64();
       for (int w = worker; w < all_work; w += num_workers) {
-        locate(cur, w);
-        for (int it = 0; it < total_kb; ++it) {
+        locate(cur, w / ksplit);
+        const int sl = w % ksplit;
+        const int it_end = (sl + 1) * total_kb / ksplit;
+        for (int it = sl * total_kb / ksplit; it < it_end; ++it) {
           const long long t0 = clock64();
           mbar_wait(empty_bar(stage), phase ^ 1u);
           t_wait += clock64() - t0;
@@ -381,13 +389,15 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       long long t_full = 0, t_tempty = 0;
       for (int w = worker; w < all_work; w += num_workers) {
         int m_blk, n_blk, n_off, width;
-        decode(w, m_blk, n_blk, n_off, width);
+        decode(w / ksplit, m_blk, n_blk, n_off, width);
         const uint32_t idesc = make_idesc_bf16(BM * CG, width, MODE == GEMM_NT ? 1 : 0, MODE == GEMM_NT ? 1 : 0);
         const long long t0 = clock64();
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         t_tempty += clock64() - t0;
         tc_fence_after();
-        for (int it = 0; it < total_kb; ++it) {
+        const int it_begin = (w % ksplit) * total_kb / ksplit;
+        const int it_end = (w % ksplit + 1) * total_kb / ksplit;
+        for (int it = it_begin; it < it_end; ++it) {
           const long long t1 = clock64();
           mbar_wait(full_bar(stage), phase);
           t_full += clock64() - t1;
@@ -414,8 +424,9 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
                 da = make_smem_desc_sw128(sah + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
                 db = make_smem_desc_sw128(sb + kk * (UMMA_K * 128), MN_ATOM_BYTES, 1024);
               }
-              if (CG == 2) umma_f16_cg2(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
-              else umma_f16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+              const uint32_t accum = (it != it_begin || kk != 0) ? 1u : 0u;
+              if (CG == 2) umma_f16_cg2(d_tmem, da, db, idesc, accum);
+              else umma_f16(d_tmem, da, db, idesc, accum);
             }
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
@@ -445,7 +456,9 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
     long long t_ph[5] = {0, 0, 0, 0, 0};  // per chunk: wait staging buffer, TMEM load, math + st.shared, proxy fence, TMA store
     for (int w = worker; w < all_work; w += num_workers) {
       int m_blk, n_blk, n_off, width;
-      const bool bias = decode(w, m_blk, n_blk, n_off, width);
+      const int wb = w / ksplit;         // base item
+      const int sl = w - wb * ksplit;    // reduction slice of this work item
+      const bool bias = decode(wb, m_blk, n_blk, n_off, width);
       const int nchunk = bias ? 0 : width / COLS;
       int tile_row0, out_batch, out_col0, seg = 0;
       if (MODE == GEMM_TN) {
@@ -511,8 +524,14 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
         tmem_ld_32x32(t_row, v0);
         tmem_ld_wait();
         if (my_row < args.d_rows) {
-          if (args.bias_out[0] != nullptr) args.bias_out[0][my_row] = args.bias_alpha[0] * __uint_as_float(v0[0]);
-          if (args.bias_out[1] != nullptr) args.bias_out[1][my_row] = args.bias_alpha[1] * __uint_as_float(v0[1]);
+          if (ksplit > 1) {  // partial sums of this slice: [slice][stream][row]
+            float* pb = args.ws_bias + static_cast<int64_t>(sl) * 2 * args.d_rows + my_row;
+            pb[0] = args.bias_alpha[0] * __uint_as_float(v0[0]);
+            pb[args.d_rows] = args.bias_alpha[1] * __uint_as_float(v0[1]);
+          } else {
+            if (args.bias_out[0] != nullptr) args.bias_out[0][my_row] = args.bias_alpha[0] * __uint_as_float(v0[0]);
+            if (args.bias_out[1] != nullptr) args.bias_out[1][my_row] = args.bias_alpha[1] * __uint_as_float(v0[1]);
+          }
         }
       }
 
@@ -614,7 +633,10 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
           }
           bulk_commit();  // every lane keeps its own (possibly empty) bulk-group sequence in scatter mode
         } else if (lane == 0) {
-          if (out_row0 < args.d_rows && col < ncols) tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
+          if (out_row0 < args.d_rows && col < ncols) {
+            if (MODE == GEMM_NT && ksplit > 1) tma_store_3d(&args.mws[seg], sbuf, col, out_row0, sl);  // partial tile
+            else tma_store_3d(&args.md[seg], sbuf, col, out_row0, out_batch);
+          }
           bulk_commit();
         }
         buf ^= 1u;
@@ -630,6 +652,98 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
       }
       if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
       t_body += clock64() - te1;
+      if (MODE == GEMM_NT && COMM == 0 && ksplit > 1) {
+        // Split reduction: this warp's slab of the item (rows tile_row0 + h * 128 .. + 32 for every h) is complete once
+        // the same warp slot of all `ksplit` slices has stored its partial.  The last to arrive adds the partials in
+        // slice order -- the same order whoever comes last -- and writes the result.
+        int last = 0;
+        __threadfence();  // bias partials are plain stores of every lane: ordered before lane 0's arrival below
+        __syncwarp();
+        if (lane == 0) {
+          bulk_wait_all<0>();           // this warp's TMA stores of the partial tile have landed
+          fence_proxy_async_all();
+          __threadfence();
+          uint32_t* cnt = args.split_count + static_cast<int64_t>(wb) * (EPI_WARPS * CG) + ew + EPI_WARPS * rank;
+          if (atomicAdd(cnt, 1u) == static_cast<uint32_t>(ksplit - 1)) {
+            atomicExch(cnt, 0u);
+            __threadfence();
+            last = 1;
+          }
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          if (bias) {
+#pragma unroll 1
+            for (int h = 0; h < MT; ++h) {
+              const int row = tile_row0 + h * BM + lane;
+              if (row < args.d_rows) {
+                float s0 = 0.f, s1 = 0.f;
+                for (int s2 = 0; s2 < ksplit; ++s2) {
+                  const float* pb = args.ws_bias + static_cast<int64_t>(s2) * 2 * args.d_rows + row;
+                  s0 += __ldcg(pb);
+                  s1 += __ldcg(pb + args.d_rows);
+                }
+                if (args.bias_out[0] != nullptr) args.bias_out[0][row] = s0;
+                if (args.bias_out[1] != nullptr) args.bias_out[1][row] = s1;
+              }
+            }
+          } else {
+            // 8 rows x 2 vectors per lane and slice in flight (the partial tiles come from L2 / HBM at ~1 us a round trip)
+            constexpr int RB = 8;
+            const float* wsb = args.ws + args.ws_seg_col[seg] + out_col0;
+            float* dst = args.d_ptr[seg] + out_col0;
+#pragma unroll 1
+            for (int h = 0; h < MT; ++h) {
+#pragma unroll 1
+              for (int r0 = 0; r0 < 32; r0 += RB) {
+                float4 acc4[RB][2];
+#pragma unroll
+                for (int i = 0; i < RB; ++i) acc4[i][0] = acc4[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int row0 = tile_row0 + h * BM + r0;
+#pragma unroll 1
+                // unconditional loads (rows / columns past the edge re-read the last valid one and are dropped at the
+                // store): nothing keeps the compiler from issuing the 16 loads of a slice back to back
+                int roff[RB], coff[2];
+#pragma unroll
+                for (int i = 0; i < RB; ++i) roff[i] = (row0 + i < args.d_rows ? row0 + i : args.d_rows - 1) * args.ws_ld;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  int c4 = 4 * (lane + 32 * j);
+                  if (c4 >= width) c4 = width - 4;
+                  if (out_col0 + c4 >= ncols) c4 = ncols - out_col0 - 4;
+                  coff[j] = c4;
+                }
+                for (int s2 = 0; s2 < ksplit; ++s2) {
+                  const float* ps = wsb + static_cast<int64_t>(s2) * args.ws_split_stride;
+                  float4 t[RB][2];
+#pragma unroll
+                  for (int i = 0; i < RB; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) t[i][j] = __ldcg(reinterpret_cast<const float4*>(ps + roff[i] + coff[j]));
+                  }
+#pragma unroll
+                  for (int i = 0; i < RB; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      acc4[i][j].x += t[i][j].x; acc4[i][j].y += t[i][j].y;
+                      acc4[i][j].z += t[i][j].z; acc4[i][j].w += t[i][j].w;
+                    }
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const int c4 = 4 * (lane + 32 * j);
+                    if (row0 + i < args.d_rows && c4 < width && out_col0 + c4 < ncols)
+                      *reinterpret_cast<float4*>(dst + static_cast<int64_t>(row0 + i) * args.d_ld[seg] + c4) = acc4[i][j];
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
       if (COMM != 0 && bias) {
         // The bias gradients of this rank are complete once every epilogue warp of every bias item has stored its
         // rows (plain stores): the last of them flags the extra ranges ready at every rank that owns a chunk of them.
@@ -776,7 +890,9 @@ int plan_schedule(GemmArgs& args, GemmMode mode, int num_sms) {
   int max_workers = num_sms / CG;
   const int cap = env_int("AVC_GEMM_MAX_WORKERS", 0);  // test knob: exercise multi-round schedules on small shapes
   if (cap > 0 && cap < max_workers) max_workers = cap;
-  const int workers = num_tiles < max_workers ? num_tiles : max_workers;
+  // every work item -- tiles and (dW) bias items -- gets its own worker while there are workers left
+  const int items = (num_tiles + (mode == GEMM_NT ? args.bias_items : 0)) * (args.ksplit > 1 ? args.ksplit : 1);
+  const int workers = items < max_workers ? items : max_workers;
   // Tail of the persistent schedule: cut the leftover tiles of the last (partial) round into narrower
   // sub-tiles when that shortens the round.  Sub-tile width >= 64 (one bf16 epilogue chunk).
   args.full_tiles = num_tiles;
@@ -817,6 +933,12 @@ cudaError_t launch_cg(const GemmArgs& args_in, GemmMode mode, GemmOut out, int n
   if (mode != GEMM_NT && args.bias_items != 0) return cudaErrorInvalidValue;
   if (mode == GEMM_NT && out == GEMM_OUT_F16) return cudaErrorInvalidValue;
   if (args.bias_items != 0 && args.bias_items != args.num_m_blocks) return cudaErrorInvalidValue;
+  if (args.ksplit < 1) args.ksplit = 1;
+  if (args.ksplit > 1) {
+    if (mode != GEMM_NT || !out_fp32 || comm || args.ws == nullptr || args.split_count == nullptr) return cudaErrorInvalidValue;
+    args.full_tiles = args.num_m_blocks * args.num_n_blocks;  // no narrow tail sub-tiles together with reduction slices
+    args.tail_split = 1;
+  }
   args.comm.poll_ns = static_cast<uint32_t>(env_int("AVC_COMM_POLL_NS", 200));
   auto run = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG, MT>::SMEM_ALLOC);
@@ -905,6 +1027,23 @@ int pick_gemm_bn(int m_blocks, const int64_t* n_extent, int nseg, int num_worker
     const double cost = static_cast<double>(rounds) * (bn + 128);
     if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
   }
+  return best;
+}
+
+int gemm_dw_splits(int base_items, int workers, int total_kb) {
+  const int forced = env_int("AVC_GEMM_KSPLIT", 0);
+  if (base_items <= 0 || workers <= 0) return 1;
+  int best = 1;
+  double best_cost = 1e30;
+  // only when the items do not fill one round of the workers: with two or more rounds the schedule is already dense and
+  // the partial tiles would cost more than the rounding they remove
+  for (int sp = 1; sp <= (base_items < workers ? 8 : 1); ++sp) {
+    if (sp > 1 && total_kb / sp < 8) break;
+    const int rounds = (base_items * sp + workers - 1) / workers;
+    const double cost = static_cast<double>(rounds) / sp + 0.04 * (sp - 1);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  if (forced >= 1 && forced <= 8 && (forced == 1 || total_kb / forced >= 1)) best = forced;
   return best;
 }
 

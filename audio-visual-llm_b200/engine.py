@@ -492,3 +492,55 @@ class HostFeeder:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self._last["free"] = ev
+
+
+class GraphedEncoder:
+    """Forward-only connector call (decode / generate, clip_whisper_model.py:1301-1340) as ONE CUDA-graph launch.
+
+    Batch-1 decoding is launch-latency bound: eager `fused_connector` costs ~0.13 ms of host work (ctypes calls, tensor
+    maps, allocator) for ~20 us of kernels.  The graph is captured once per input signature on static input buffers;
+    a call copies the new inputs into them (device-to-device, stream-ordered) and replays the graph: the kernel
+    parameters -- including the TMA tensor maps, which live in kernel parameter space -- are baked into the graph, so
+    nothing is re-encoded.  Outputs are static tensors that the next call overwrites.
+
+        enc = GraphedEncoder(lambda a, v, ids: fused_connector(a, v, wa, ba, wv, bv, plan, prompt_ids=ids, ...))
+        emb, mask, _ = enc(audio_feats, video_feats, prompt_ids)
+
+    The captured callable must be free of host synchronisation (`check=False`) and run under `torch.no_grad()`; weights
+    it closes over are read at replay time (the bf16 pack is part of the graph when the pack cache is cold, so call
+    `connector_ops.invalidate_pack_cache()` + `reset()` after the weights change)."""
+
+    def __init__(self, fn, warmup: int = 2):
+        self.fn = fn
+        self.warmup = warmup
+        self._graphs = {}
+
+    @staticmethod
+    def _key(inputs):
+        return tuple(None if t is None else (tuple(t.shape), t.dtype, t.device) for t in inputs)
+
+    def reset(self) -> None:
+        self._graphs.clear()
+
+    def __call__(self, *inputs):
+        key = self._key(inputs)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = [None if t is None else t.clone() for t in inputs]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(self.warmup):   # lazy module loading, pack cache, allocator warm-up: outside the capture
+                    self.fn(*static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                static_out = self.fn(*static_in)
+            entry = (graph, static_in, static_out)
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        for dst, src in zip(static_in, inputs):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return static_out

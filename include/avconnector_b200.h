@@ -124,7 +124,14 @@ AVC_API int avc_proj_bwd_dw(const avc_mat* dy /* bf16 [b][rows][H] */, int32_t d
  * `present` is a bf16 [batches][rows >= x rows][64] matrix whose column i is 1 where row r of sample b carries a
  * token of stream i and 0 elsewhere (all ones for dense streams; the zero-padded rows of the shorter stream are what
  * clip_whisper_model.py:340-345 pads AFTER the projection, so they must not see that stream's bias).  Columns 2..63
- * are ignored.  Replaces autograd's db = sum dY of nn.Linear (modality_connector.py:32); deterministic. */
+ * are ignored.  Replaces autograd's db = sum dY of nn.Linear (modality_connector.py:32); deterministic.
+ *
+ * Split reduction.  When the launch has fewer work items than the GPU has CTA pairs (short K_s: 8 x 5 tiles at 1280 ->
+ * 4096), every item is cut into S <= 8 slices of the row reduction that run on the idle pairs; slices store partial tiles
+ * in `workspace` and the last slice to finish a 32-row slab adds the partials IN SLICE ORDER (deterministic) into dW /
+ * db.  avc_proj_bwd_dw_plan reports S and the bytes needed for the given operands; zero-fill the workspace once after
+ * allocating it (256-byte aligned; every launch leaves its arrival counters zero).  workspace == NULL, or bias == NULL
+ * for dW alone, are allowed; a workspace that is too small lowers S. */
 typedef struct avc_bias_grad {
   const avc_mat* present;  /* bf16 [batches][rows][64] */
   float* out0;             /* [H] fp32 or NULL */
@@ -132,8 +139,10 @@ typedef struct avc_bias_grad {
   float alpha0, alpha1;
 } avc_bias_grad;
 AVC_API int avc_proj_bwd_dw_db(const avc_mat* dy, int32_t dy_row_base, int32_t nseg, const avc_mat* x,
-                               const avc_mat* dw, const float* alpha, const avc_bias_grad* bias, int32_t max_sms,
-                               void* stream);
+                               const avc_mat* dw, const float* alpha, const avc_bias_grad* bias /* or NULL */,
+                               void* workspace /* or NULL */, size_t workspace_bytes, int32_t max_sms, void* stream);
+AVC_API int avc_proj_bwd_dw_plan(const avc_mat* dy, int32_t nseg, const avc_mat* x, int32_t with_bias,
+                                 int32_t* splits, size_t* workspace_bytes);
 
 /* ---- projector backward: input gradient (unfrozen towers, freeze_encoders=False: clip_whisper_model.py:1096,1136)
  * dX[b, r, :] = sum_s dY[b, r, :] . W_s   computed as the forward GEMM with B = W_s^T from avc_pack_weight_t

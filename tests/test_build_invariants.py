@@ -53,7 +53,8 @@ def test_light_splice_fits_next_to_the_forward_gemm(avc):
     # forward GEMM CTA: 6 x 32 KB stages + 32 KB epilogue staging + 256 B barriers + 1 KB alignment slack of dynamic
     # shared memory, plus the 1 KB the driver reserves per CTA; an SM has 228 KB
     gemm_smem = 6 * 32768 + 32768 + 256 + 1024 + 1024
-    fwd = {k: v for k, v in res.items() if re.search(r"gemm_kernelILi0ELi[012]ELi2ELi1ELi0E", k)}
+    # forward kernels the fused step can launch: TN, any output type, CTA pairs, MT = 1, no comm, ACT = 0
+    fwd = {k: v for k, v in res.items() if re.search(r"gemm_kernelILi0ELi[012]ELi2ELi1ELi0ELi0E", k)}
     assert len(fwd) == 3, sorted(res)
     for v in light:
         # cuobjdump's SHARED already contains the 1 KB per-CTA reservation of the small kernel

@@ -88,6 +88,51 @@ def test_dw_db_one_launch_matches_fp64_and_colsum(avc, cuda_dev, monkeypatch, B,
     assert all(torch.equal(a_, b_) for a_, b_ in zip(dws, d2)) and torch.equal(db0, e0) and torch.equal(db1, e1)
 
 
+@pytest.mark.parametrize("forced", [0, 2, 3, 8])
+def test_dw_split_reduction_is_deterministic_and_matches_fp64(avc, cuda_dev, monkeypatch, forced):
+    """Few tiles (2 x 3 + 2 bias items on 74 CTA pairs): the row reduction is cut into slices whose partial tiles are
+    added in slice order by the last finisher.  Forced slice counts and the planner's own choice; dW, db against
+    fp64; two launches give the same bits; the workspace counters are left zero; same values as the unsplit launch."""
+    L = avc._lib
+    if forced:
+        monkeypatch.setenv("AVC_GEMM_KSPLIT", str(forced))
+    g = torch.Generator().manual_seed(17)
+    dev = cuda_dev
+    B, N, P, H, Ka, Kv = 5, 530, 3, 1000, 512, 200   # H, Kv not multiples of the tile: row / column guards
+    dy = torch.randn(B, P + N, H, generator=g).to(dev, torch.bfloat16)
+    xs = [torch.randn(B, N, Ka, generator=g).to(dev, torch.bfloat16), torch.randn(B, N, Kv, generator=g).to(dev, torch.bfloat16)]
+    present = L.present_operand(B, N, dev)
+    splits, nbytes = L.dw_plan(dy, xs, True)
+    if forced:
+        assert splits == forced and nbytes > 0
+    else:
+        assert splits > 1, "8 work items on 74 workers: the planner must split"
+    outs = []
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    for rep in range(2):
+        dws = [torch.full((H, x.shape[2]), float("nan"), device=dev) for x in xs]
+        db0, db1 = torch.full((H,), float("nan"), device=dev), torch.full((H,), float("nan"), device=dev)
+        L.proj_bwd_dw(dy, xs, dws, [0.5, 2.0], dy_row_base=P, bias=(present, db0, db1, 0.5, 2.0), workspace=ws)
+        torch.cuda.synchronize()
+        outs.append((dws, db0, db1))
+    dy64 = dy[:, P:].double()
+    for x, dw, a in zip(xs, outs[0][0], [0.5, 2.0]):
+        assert rel_err(dw, a * torch.einsum("bnh,bnk->hk", dy64, x.double())) <= 2e-5
+    assert rel_err(outs[0][1], 0.5 * dy64.sum((0, 1))) <= 2e-5 and rel_err(outs[0][2], 2.0 * dy64.sum((0, 1))) <= 2e-5
+    for a_, b_ in zip(outs[0][0] + [outs[0][1], outs[0][2]], outs[1][0] + [outs[1][1], outs[1][2]]):
+        assert torch.equal(a_, b_), "slice-order summation: same bits every launch"
+    counters = ws[:8 * 8 * 4].view(torch.int32)   # (6 tiles + 2 bias items) x 8 warp slots
+    assert int(counters.abs().max()) == 0, "every launch leaves its arrival counters zero"
+    # unsplit launch: same values up to fp32 re-association
+    monkeypatch.setenv("AVC_GEMM_KSPLIT", "1")
+    d1 = [torch.empty_like(t) for t in outs[0][0]]
+    e0, e1 = torch.empty_like(outs[0][1]), torch.empty_like(outs[0][2])
+    L.proj_bwd_dw(dy, xs, d1, [0.5, 2.0], dy_row_base=P, bias=(present, e0, e1, 0.5, 2.0), split=False)
+    torch.cuda.synchronize()
+    for a_, b_ in zip(outs[0][0] + [outs[0][1], outs[0][2]], d1 + [e0, e1]):
+        assert rel_err(a_, b_) <= 2e-5
+
+
 def test_dw_db_with_row_flags_operand(avc, cuda_dev):
     """Packed rows + uint8 row flags (what the gather writes) -> present operand -> db of each stream."""
     L = avc._lib
@@ -600,3 +645,30 @@ def test_engine_at_full_size_passes_the_bench_self_check(avc, cuda_dev, config):
     assert eng.direct == (config == "cfg2")
     if config == "cfg4":
         assert eng.ragged and eng.M == sum(eng.counts) and min(eng.counts) >= 100 and max(eng.counts) <= 400
+
+
+def test_graphed_encoder_replays_the_eager_bits(avc, cuda_dev):
+    """Forward-only fast path: one CUDA-graph launch per encode (decode / generate); new inputs, same graph."""
+    from audio_visual_llm_b200.engine import GraphedEncoder
+
+    g = torch.Generator().manual_seed(61)
+    B, Ta, Tv, Da, Dv, H, P, V = 1, 40, 20, 64, 32, 128, 4, 50
+    wa, ba, wv, bv = (t.to(cuda_dev) for t in _rand_params(g, H, 4 * Da, 2 * Dv))
+    table = torch.randn(V, H, generator=g).to(cuda_dev, torch.bfloat16)
+    plan = avc.FusePlan(fusion="concat", audio_stride=4, video_stride=2, max_seq_len=64)
+
+    def enc(a, v, ids):
+        return avc.fused_connector(a, v, wa, ba, wv, bv, plan, prompt_ids=ids, embed_table=table,
+                                   out_dtype=torch.bfloat16)
+
+    graphed = GraphedEncoder(enc)
+    for trial in range(3):
+        a = torch.randn(B, Ta, Da, generator=g).to(cuda_dev, torch.bfloat16)
+        v = torch.randn(B, Tv, Dv, generator=g).to(cuda_dev, torch.bfloat16)
+        ids = torch.randint(1, V, (B, P), generator=g).to(cuda_dev)
+        with torch.no_grad():
+            emb, mask, _ = enc(a, v, ids)
+        gemb, gmask, _ = graphed(a, v, ids)
+        torch.cuda.synchronize()
+        assert torch.equal(gemb, emb) and torch.equal(gmask, mask), trial
+    assert len(graphed._graphs) == 1, "one capture serves every call with the same input signature"

@@ -16,6 +16,9 @@ L = pkg._lib
 dev = torch.device("cuda:0")
 B, N, P, H, Ka, Kv = 32, 375, 16, 4096, 4096, 2048
 M, K = B * N, Ka + Kv
+if len(sys.argv) > 1:   # M,Ka,Kv,H of another shape, e.g. cfg3: 96000,1280,0,4096
+    M, Ka, Kv, H = (int(x) for x in sys.argv[1].split(","))
+    K = Ka + Kv
 A = torch.randn(M, K, device=dev).to(torch.bfloat16)
 W = (torch.randn(H, K, device=dev) / K ** 0.5).to(torch.bfloat16)
 bias = torch.randn(H, device=dev)
@@ -57,5 +60,21 @@ def run(name, fn, iters=20):
     print(json.dumps(rec), flush=True)
 
 
-run("proj_fwd", lambda: L.proj_fwd([A[:, :Ka], A[:, Ka:]], [W[:, :Ka], W[:, Ka:]], Y, bias0=bias, bias1=bias))
-run("proj_bwd_dw", lambda: L.proj_bwd_dw(dY, [A], [dW], [1.0]))
+if Kv:
+    run("proj_fwd", lambda: L.proj_fwd([A[:, :Ka], A[:, Ka:]], [W[:, :Ka], W[:, Ka:]], Y, bias0=bias, bias1=bias))
+    run("proj_bwd_dw", lambda: L.proj_bwd_dw(dY, [A[:, :Ka], A[:, Ka:]], [dW[:, :Ka], dW[:, Ka:]], [1.0, 1.0]))
+else:
+    run("proj_fwd", lambda: L.proj_fwd([A], [W], Y, bias0=bias))
+    run("proj_bwd_dw", lambda: L.proj_bwd_dw(dY, [A], [dW], [1.0]))
+for name, fn in (("cublas_fwd", lambda: torch.matmul(A, W.t(), out=Y)),
+                 ("cublas_dw", lambda: torch.matmul(dY.t(), A))):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"kernel": name, "ms": round(s.elapsed_time(e) / 20, 4)}), flush=True)
