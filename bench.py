@@ -332,6 +332,24 @@ def self_check(torch, dist, eng, world, dev, n_rows=64, n_side=32):
 
 
 # ---------------------------------------------------------------------------------------------- eager torch / cuBLAS
+def graphed_leg(torch, eng, steps):
+    """The same step replayed as one CUDA graph (engine.ConnectorStep.capture_graph): what is left when the host-side
+    launch cost is taken out.  Single process only."""
+    graph = eng.capture_graph()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        graph.replay()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    return {"ms_per_step": ms, "value": eng.fused_tokens / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "what": "the whole step (all launches, side-stream work included) captured once and replayed as one CUDA graph"}
+
+
 def gpu_eager_leg(torch, eng, iters=20):
     """The reference connector's semantics as eager PyTorch (bf16 autocast, cuBLAS GEMMs) on the same GPU, same shapes,
     same inputs: per-modality nn.Linear, pad, weighted sum, prompt-embedding cat, ones mask, label rule, autograd
@@ -649,9 +667,14 @@ def main():
     }
     kernels = {k: v for k, v in kernels.items() if v is not None}
 
+    graphed = None
+    if world == 1 and not args.no_extras:
+        graphed = graphed_leg(torch, eng, max(20, min(args.steps, 200)))
     gpu_eager = None
     if not args.no_extras:
-        gpu_eager = gpu_eager_leg(torch, eng)
+        # as many iterations as the timed region had steps (bounded), so that the eager / cuBLAS numbers are taken in the
+        # same clock regime (burst for the driver's 20 steps, power-capped for long runs) as the ones they sit beside
+        gpu_eager = gpu_eager_leg(torch, eng, iters=max(20, min(args.steps, 300)))
         if gpu_eager is not None:
             gpu_eager["ours_over_eager_step"] = gpu_eager["ms_per_step"] / ms_per_step
             gpu_eager["ours_over_cublas"] = {"fwd": gpu_eager["cublas"]["fwd_ms"] / kernel_ms["proj_fwd"],
@@ -699,7 +722,8 @@ def main():
                    "parallelism": f"dp{world}", "step": step_desc, "collective": collective,
                    "l2": "no flush: one step streams several times the 126 MB L2 (features, W, embeds, grads)"},
         "roofline": roofline, "kernels": kernels, "per_rank_kernel_ms": per_rank, "sustained": sustained,
-        "self_check": check, "gpu_eager": gpu_eager, "strong_scaling": strong, "unfused_step": unfused,
+        "self_check": check, "gpu_eager": gpu_eager, "graphed": graphed, "strong_scaling": strong,
+        "unfused_step": unfused,
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": eng.launches_per_step * args.steps,
     }

@@ -79,6 +79,7 @@ def run_bench(argv, world, fused, mc):
     with mock.patch.dict("os.environ", env), mock.patch.object(sys, "argv", ["bench.py"] + argv), \
             mock.patch.object(E, "ConnectorStep", FakeEngine), mock.patch("torch.cuda.set_device"), \
             mock.patch.object(bench, "self_check", lambda *a, **k: dict(fake_check)), \
+            mock.patch.object(bench, "graphed_leg", lambda *a, **k: {"ms_per_step": 50.0, "value": 2.0}), \
             mock.patch.object(bench, "gpu_eager_leg", lambda *a, **k: dict(fake_eager, cublas=dict(fake_eager["cublas"]))), \
             mock.patch("torch.cuda.Event", FakeEvent), mock.patch("torch.cuda.synchronize"), \
             mock.patch("torch.cuda.empty_cache"), mock.patch("torch.device", lambda *a: "cpu"), \
