@@ -765,11 +765,23 @@ def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
     from audio_visual_llm_b200.engine import HostFeeder
     from audio_visual_llm_b200.parallel import FusedGradSync
 
+    from audio_visual_llm_b200 import numa
+
     s = eng.shape
-    audio_h = eng.audio.cpu().pin_memory() if eng.use_a else None
-    video_h = eng.video.cpu().pin_memory() if eng.use_v else None
-    ids_h = eng.input_ids.cpu().pin_memory()
-    labels_h = eng.labels_in.cpu().pin_memory()
+    # input buffers on the GPU's own NUMA node when the host exposes one (pool boxes are single-node KVM guests:
+    # "unbound:no NUMA choice", profiles/r02_h2d_numa_probe_n4.log)
+    node = numa.gpu_numa_node(dev.index if dev.index is not None else torch.cuda.current_device())
+    placement = []
+
+    def pin(t):
+        buf, how = numa.pin_like(t.cpu(), node)
+        placement.append(how)
+        return buf
+
+    audio_h = pin(eng.audio) if eng.use_a else None
+    video_h = pin(eng.video) if eng.use_v else None
+    ids_h = pin(eng.input_ids)
+    labels_h = pin(eng.labels_in)
     wa, ba, wv, bv = ((t.clone().requires_grad_(True) if t is not None else None)
                       for t in (eng.wa, eng.ba, eng.wv, eng.bv))
     mask_h = torch.empty(s.batch, eng.S, dtype=torch.int64).pin_memory()
@@ -862,6 +874,9 @@ def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
     ms_copy = timed(copies) / n_probe
     if sync is not None:
         sync.close()
+    for t in (audio_h, video_h, ids_h, labels_h):
+        if t is not None:
+            numa.release(t)
     collective = "none" if world == 1 else (
         "fused into the dW GEMM launch through parallel.FusedGradSync (the parameters' .grad are views of the peer-mapped "
         "bucket)" if sync.fused else "NCCL all-reduce of the flat bucket")
@@ -869,6 +884,7 @@ def run_e2e(torch, dist, pkg, eng, plan, dev, args, world):
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "collective": collective,
             "h2d_only_ms_per_step": ms_copy, "h2d_only_GBps_per_gpu": h2d / ms_copy / 1e6,
             "h2d_GBps_per_gpu_in_e2e": h2d / ms_step / 1e6,
+            "host_numa": {"gpu_node": node, "nodes": numa.nodes(), "pinned_placement": sorted(set(placement))},
             "api": "HostFeeder (pinned host -> device, double-buffered on a copy stream) -> fused_connector(...) -> "
                    "emb.backward(dLLM) -> D2H of masks / labels / bias grads; every step's H2D is inside the timed region; "
                    "h2d_only_* = the same copies alone on every rank at once (the host-side ceiling of this box)"}

@@ -183,3 +183,26 @@ def test_fd_passing_between_threads(tmp_path, monkeypatch):
             parallel._fetch_fd(tag + "_nobody", timeout_s=0.2)
     finally:
         os.close(fd)
+
+
+def test_numa_helpers_topology_and_binding(avc):
+    """numa.py: sysfs parsing, and -- where the kernel allows mbind -- that the pages really land on the node."""
+    import ctypes
+
+    from audio_visual_llm_b200 import numa
+
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    ns = numa.nodes()
+    assert ns == sorted(ns)
+    if not ns:
+        pytest.skip("no NUMA nodes in sysfs")
+    assert all(len(numa.node_cpus(n)) > 0 for n in ns)
+    t = torch.empty(1 << 22, dtype=torch.uint8)
+    err = numa._mbind(t.data_ptr(), t.nbytes, ns[0])
+    ctypes.memset(t.data_ptr(), 0, t.nbytes)
+    placed = numa.pages_on_node(t)
+    if err == 0 and placed:
+        assert placed.get(ns[0], 0) >= (1 << 22) // 4096 and sum(placed.values()) == placed[ns[0]]
+    with numa.cpus_of_node(ns[0]) as n:
+        assert n >= 0
