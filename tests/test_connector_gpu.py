@@ -606,3 +606,105 @@ def test_rate_alignment_at_stride_one_repeats_video_frames(avc, cuda_dev):
                 _provided_clip=StubClip(Dv).to(dev))
     m = avc.ClipWhisperModel(**m_kw)
     assert (m.audio_stride, m.video_stride, m.video_repeat) == (1, 1, 2) and m._plan().video_repeat == 2
+
+
+def _random_case(seed):
+    """One seeded configuration of the fused connector: modality, fusion, strides, ragged or dense, widths that are
+    multiples of 8 only, any LLM dtype, with or without a prompt / input gradients."""
+    g = torch.Generator().manual_seed(1000 + seed)
+
+    def pick(seq):
+        return seq[int(torch.randint(0, len(seq), (1,), generator=g))]
+
+    c = SimpleNamespace(seed=seed, g=g)
+    c.modality = pick(["audio", "video", "both", "both"])
+    c.fusion = pick(["sum", "concat"])
+    c.ka, c.kv = pick([1, 2, 4]), pick([1, 2])
+    c.B = pick([1, 2, 3, 5])
+    c.Ta, c.Tv = pick([5, 16, 33, 70]), pick([3, 8, 20, 41])
+    c.Da, c.Dv = 8 * pick([1, 3, 8, 12]), 8 * pick([1, 2, 5, 8])
+    c.H = 8 * pick([1, 9, 16, 33, 40])
+    c.fs = pick([0.5, 0.25, 0.8])
+    c.out_dtype = pick([torch.bfloat16, torch.bfloat16, torch.float32, torch.float16])
+    c.ragged = pick([False, True])
+    c.P = pick([0, 3, 7])
+    c.dx = pick([False, False, True])
+    c.max_seq_len = pick([256, 12])
+    return c
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_randomised_configurations_vs_oracle(avc, cuda_dev, seed):
+    """Seeded sweep over the connector's configuration space (the product of what the other tests fix one at a time):
+    outputs, masks, labels, parameter gradients and -- when the features require grad -- input gradients against the
+    CPU oracle.  Index / mask / label / copied-row results bit-exact; projected values within REL_TOL / COS_TOL."""
+    c = _random_case(seed)
+    g, dev = c.g, cuda_dev
+    use_a, use_v = c.modality in ("audio", "both"), c.modality in ("video", "both")
+    V, PH = 50, 49
+    # bf16-representable inputs / weights so that the comparison measures the kernels, not the input rounding
+    a = torch.randn(c.B, c.Ta, c.Da, generator=g).bfloat16().float() if use_a else None
+    v = torch.randn(c.B, c.Tv, c.Dv, generator=g).bfloat16().float() if use_v else None
+    wa, ba, wv, bv = _rand_params(g, c.H, c.ka * c.Da, c.kv * c.Dv)
+    table = torch.randn(V, c.H, generator=g).to(c.out_dtype)
+    spec = O.ConnectorSpec(modality=c.modality, fusion=c.fusion, fusion_scale=c.fs, audio_stride=c.ka,
+                           video_stride=c.kv, max_seq_len=c.max_seq_len, mask_mode=1, label_mode=1)
+    plan = avc.FusePlan(modality=c.modality, fusion=c.fusion, fusion_scale=c.fs, audio_stride=c.ka, video_stride=c.kv,
+                        max_seq_len=c.max_seq_len, mask_mode=1, label_mode=1)
+    N = plan.tokens(c.Ta if use_a else None, c.Tv if use_v else None)
+    la = lv = None
+    if c.ragged:
+        la = [int(torch.randint(0, c.Ta + 1, (1,), generator=g)) for _ in range(c.B)] if use_a else None
+        lv = [int(torch.randint(0, c.Tv + 1, (1,), generator=g)) for _ in range(c.B)] if use_v else None
+        ntok = [plan.tokens(la[b] if use_a else None, lv[b] if use_v else None) for b in range(c.B)]
+    else:
+        ntok = [N] * c.B
+    S = c.P + max(max(ntok), 1) + 2
+    ids = torch.zeros(c.B, S, dtype=torch.int64)
+    for b, n in enumerate(ntok):
+        row = torch.randint(1, PH, (S,), generator=g)
+        row[c.P:c.P + n] = PH
+        row[c.P + n + 1:] = 0   # one text id after the AV run, then padding
+        ids[b] = row
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in (a, v, wa, ba, wv, bv)]
+    a_c, v_c, wa_c, ba_c, wv_c, bv_c = leaves
+    tok, _ = O.connector_tokens(a_c, v_c, wa_c, ba_c, wv_c, bv_c, spec,
+                                audio_valid=torch.tensor(la) if la is not None else None,
+                                video_valid=torch.tensor(lv) if lv is not None else None)
+    emb_r, mask_r, lab_r = O.splice_tokens(tok, ids, PH, table.float(), 0, spec, ntok=torch.tensor(ntok))
+    up = torch.randn(emb_r.shape, generator=g)
+    if emb_r.requires_grad:
+        (emb_r * up).sum().backward()
+
+    def dev_leaf(t, grad):
+        return None if t is None else t.to(dev).requires_grad_(grad)
+
+    a_d, v_d = dev_leaf(a, c.dx), dev_leaf(v, c.dx)
+    wa_d, ba_d, wv_d, bv_d = (dev_leaf(t, True) for t in (wa, ba, wv, bv))
+    emb, mask, lab = avc.fused_connector(a_d, v_d, wa_d if use_a else None, ba_d if use_a else None,
+                                         wv_d if use_v else None, bv_d if use_v else None, plan,
+                                         input_ids=ids.to(dev), placeholder_id=PH, embed_table=table.to(dev),
+                                         out_dtype=c.out_dtype, audio_lengths=la, video_lengths=lv, check=True)
+    assert emb.dtype == c.out_dtype
+    (emb.float() * up.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    is_ph = ids == PH
+    what = f"seed {seed}: {vars(c)}"
+    if is_ph.any():
+        assert_close(emb[is_ph.to(dev)].float(), emb_r[is_ph], "AV rows, " + what)
+    assert torch.equal(emb.cpu()[~is_ph], emb_r[~is_ph].to(c.out_dtype)), what
+    assert torch.equal(mask.cpu(), mask_r) and torch.equal(lab.cpu(), lab_r), what
+    pairs = []
+    if use_a:
+        pairs += [(wa_d, wa_c, "dWa"), (ba_d, ba_c, "dba")]
+    if use_v:
+        pairs += [(wv_d, wv_c, "dWv"), (bv_d, bv_c, "dbv")]
+    if c.dx:
+        pairs += [(t_d, t_c, n) for t_d, t_c, n in ((a_d, a_c, "dA"), (v_d, v_c, "dV")) if t_d is not None]
+    for got, ref, name in pairs:
+        ref_g = ref.grad if ref.grad is not None else torch.zeros_like(ref)
+        got_g = got.grad if got.grad is not None else torch.zeros_like(got)
+        if float(ref_g.abs().max()) == 0.0:
+            assert float(got_g.abs().max()) == 0.0, f"{name} must be zero, {what}"
+        else:
+            assert_close(got_g, ref_g, f"{name}, {what}")
