@@ -177,6 +177,7 @@ class ConnectorStep:
         # packs + {[gather] gemm splice [splice_bwd] gemm} [+ colsum]
         self.launches_per_step = npack + (3 if self.direct else 5) + (0 if self.bias_in_gemm else 1)
         self.events = None  # optional per-kernel CUDA events, see enable_kernel_timing()
+        self.optimizer = None  # set by attach_optimizer(): train_step() then runs clip + AdamW after the backward
         self.nvtx = os.environ.get("AVC_NVTX", "0") == "1"
         # N > 1: optionally all-reduce the audio-weight span while the video-weight dW launch still runs.  Measured on
         # B200 x8 (profiles/README.md): NCCL needs ~48+ SMs to run at speed, which the persistent GEMM must give up, so
@@ -253,14 +254,54 @@ class ConnectorStep:
             done.record(side)
         return done
 
-    def forward(self):
-        p = self.plan
+    def _named_params(self):
+        named = []
+        if self.use_a:
+            named += [("audio_connector.linear.weight", self.wa), ("audio_connector.linear.bias", self.ba)]
+        if self.use_v:
+            named += [("video_connector.linear.weight", self.wv), ("video_connector.linear.bias", self.bv)]
+        return named
+
+    def _pack_weights(self):
         col = 0
         if self.use_a:
             L.pack_weight(self.wa, self.wp[:, :self.Ka], self.sa)
             col = self.Ka
         if self.use_v:
             L.pack_weight(self.wv, self.wp[:, col:], self.sv)
+
+    def attach_optimizer(self, **adamw_kwargs):
+        """Make `train_step()` a full trainer step (clip_whisper_trainer.py:453-464): forward, backward (+ all-reduce),
+        global-norm clip and AdamW on the flat gradient bucket.  The AdamW kernel also writes the bf16, fusion-scaled
+        copy of each updated weight straight into the packed GEMM operand, so the forward's two pack launches go away."""
+        from .trainer_step import ConnectorAdamW
+
+        opt = ConnectorAdamW(self._named_params(), bucket=self.bucket, **adamw_kwargs)
+        if self.use_a:
+            opt.attach_packed("audio_connector.linear.weight", self.wp[:, :self.Ka], self.sa)
+        if self.use_v:
+            opt.attach_packed("video_connector.linear.weight", self.wp[:, (self.Ka if self.use_a else 0):], self.sv)
+        self._pack_weights()   # the pack of the current weights; from here on the optimizer keeps it current
+        self.optimizer = opt
+        return opt
+
+    def detach_optimizer(self):
+        self.optimizer = None
+
+    def train_step(self, other_sumsq=None):
+        """forward + backward (+ gradient all-reduce) + clip + AdamW; `other_sumsq` = the squared gradient norm of the
+        non-connector parameters (LoRA), a device scalar, for the reference's GLOBAL clip."""
+        if self.optimizer is None:
+            raise L.ConnectorError("train_step() needs attach_optimizer() first")
+        self.forward()
+        g = self.backward(True)
+        self.optimizer.step(other_sumsq=other_sumsq)
+        return g
+
+    def forward(self):
+        p = self.plan
+        if self.optimizer is None:
+            self._pack_weights()
         if not self.direct:
             self._timed("gather", lambda: L.gather_fwd(self.audio, self.video, p.audio_stride, p.video_stride,
                                                        self.shape.batch, self.N, self.A, self.flags,

@@ -332,6 +332,37 @@ def self_check(torch, dist, eng, world, dev, n_rows=64, n_side=32):
 
 
 # ---------------------------------------------------------------------------------------------- eager torch / cuBLAS
+def trainer_leg(torch, dist, eng, steps, world):
+    """The reference's whole trainer step for the connector parameters (clip_whisper_trainer.py:453-464): forward,
+    backward, gradient all-reduce, global-norm clip, AdamW -- `ConnectorStep.train_step()`.  The AdamW kernel writes the
+    bf16 pack of the updated weights, so the forward's pack launches disappear.  All ranks run it; max over ranks."""
+    params = eng.attach_optimizer(lr=1e-6).params   # a tiny rate: the weights stay where the other legs expect them
+    for _ in range(3):
+        eng.train_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.train_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if eng.bucket.peer is not None:
+        eng.bucket.peer.check()
+    eng.detach_optimizer()
+    npack = int(eng.use_a) + int(eng.use_v)
+    return {"ms_per_step": ms, "value": eng.fused_tokens * world / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "launches_per_step": eng.launches_per_step - npack + 2 + len(params),
+            "what": "fwd + bwd (+ fused gradient all-reduce) + global-norm clip + AdamW on the flat bucket "
+                    "(ConnectorStep.train_step); the optimizer kernel emits the bf16 weight pack of the next forward"}
+
+
 def graphed_leg(torch, eng, steps):
     """The same step replayed as one CUDA graph (engine.ConnectorStep.capture_graph): what is left when the host-side
     launch cost is taken out.  Single process only."""
@@ -624,6 +655,11 @@ def main():
     if world > 1 and not args.global_batch and args.config == "cfg2" and not args.no_extras and 256 % world == 0:
         strong = strong_scaling_block(torch, dist, pkg, w, dev, rank, world, eng, ms_per_step, args)
 
+    # ------------------------------------------------------------------ the trainer step (clip + AdamW) beside it
+    trainer = None
+    if not args.no_extras:
+        trainer = trainer_leg(torch, dist, eng, max(20, min(args.steps, 200)), world)
+
     # ------------------------------------------------------------------ end to end from pinned host tensors
     e2e = None
     if not args.no_e2e:
@@ -723,6 +759,7 @@ def main():
                    "l2": "no flush: one step streams several times the 126 MB L2 (features, W, embeds, grads)"},
         "roofline": roofline, "kernels": kernels, "per_rank_kernel_ms": per_rank, "sustained": sustained,
         "self_check": check, "gpu_eager": gpu_eager, "graphed": graphed, "strong_scaling": strong,
+        "trainer_step": trainer,
         "unfused_step": unfused,
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": eng.launches_per_step * args.steps,

@@ -79,6 +79,7 @@ def run_bench(argv, world, fused, mc):
     with mock.patch.dict("os.environ", env), mock.patch.object(sys, "argv", ["bench.py"] + argv), \
             mock.patch.object(E, "ConnectorStep", FakeEngine), mock.patch("torch.cuda.set_device"), \
             mock.patch.object(bench, "self_check", lambda *a, **k: dict(fake_check)), \
+            mock.patch.object(bench, "trainer_leg", lambda *a, **k: {"ms_per_step": 120.0, "value": 1.5}), \
             mock.patch.object(bench, "graphed_leg", lambda *a, **k: {"ms_per_step": 50.0, "value": 2.0}), \
             mock.patch.object(bench, "gpu_eager_leg", lambda *a, **k: dict(fake_eager, cublas=dict(fake_eager["cublas"]))), \
             mock.patch("torch.cuda.Event", FakeEvent), mock.patch("torch.cuda.synchronize"), \
@@ -98,7 +99,7 @@ def run_bench(argv, world, fused, mc):
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches",
-             "sustained", "self_check", "gpu_eager", "strong_scaling"}
+             "sustained", "self_check", "gpu_eager", "strong_scaling", "trainer_step"}
 
 
 @pytest.mark.parametrize("argv,world,fused,mc,scaling,collective", [
@@ -117,7 +118,7 @@ def test_bench_line(avc, argv, world, fused, mc, scaling, collective):
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert d["roofline"]["bound"] == "tensor" and d["roofline"]["unit"] == "TFLOP/s"
     assert d["gpu_launches"] == 5 * 5
-    assert d["self_check"]["ok"] is True
+    assert d["self_check"]["ok"] is True and d["trainer_step"]["ms_per_step"] > 0
     assert {"steps", "ms_per_step", "value", "clocks", "roofline"} <= set(d["sustained"])
     assert d["gpu_eager"]["ours_over_eager_step"] > 0 and set(d["gpu_eager"]["ours_over_cublas"]) == {"fwd", "dw"}
     if world > 1 and scaling == "weak":

@@ -63,3 +63,41 @@ def test_adamw_with_global_clip_matches_torch(avc, cuda_dev, other_norm):
     exp = torch.cat([(dev["audio_connector.linear.weight"] * sa).bfloat16(),
                      (dev["video_connector.linear.weight"] * torch.tensor(1 - sa, dtype=torch.float32)).bfloat16()], 1)
     assert torch.equal(packed.view(torch.int16), exp.view(torch.int16))
+
+
+@pytest.mark.parametrize("fuse_gather", [True, False])
+def test_engine_train_step_equals_step_then_optimizer(avc, cuda_dev, fuse_gather):
+    """ConnectorStep.train_step() (optimizer attached: AdamW emits the bf16 weight pack, the forward skips its pack
+    launches) must leave the same weights, bit for bit, as step() followed by a stand-alone ConnectorAdamW.step()."""
+    from audio_visual_llm_b200.engine import ConnectorStep, StepShape
+    from audio_visual_llm_b200.trainer_step import ConnectorAdamW
+
+    L = avc._lib
+    shape = StepShape(batch=3, audio_frames=40, video_frames=20, audio_dim=32, video_dim=16, hidden=128, prompt_len=5,
+                      vocab=100)
+    plan = avc.FusePlan(fusion="concat", audio_stride=4, video_stride=2, max_seq_len=64)
+    a = ConnectorStep(shape, plan, cuda_dev, seed=5, fuse_gather=fuse_gather)
+    b = ConnectorStep(shape, plan, cuda_dev, seed=5, fuse_gather=fuse_gather)
+    kw = dict(lr=1e-2, weight_decay=0.01, max_grad_norm=0.5)
+    a.attach_optimizer(**kw)
+    opt_b = ConnectorAdamW(b._named_params(), bucket=b.bucket, **kw)
+    w0 = a.wa.clone()
+    for _ in range(3):
+        a.train_step()
+        b.step()
+        opt_b.step()
+    torch.cuda.synchronize()
+    assert not torch.equal(a.wa, w0), "the optimizer must have moved the weights"
+    for (n, pa), (_, pb) in zip(a._named_params(), b._named_params()):
+        assert torch.equal(pa, pb), n
+    assert torch.equal(a.emb, b.emb) and torch.equal(a.bucket.flat, b.bucket.flat)
+    # the pack the optimizer maintains is exactly what the forward's own pack kernel would produce
+    ref = torch.empty_like(a.wp)
+    L.pack_weight(a.wa, ref[:, :a.Ka], a.sa)
+    L.pack_weight(a.wv, ref[:, a.Ka:], a.sv)
+    assert torch.equal(ref, a.wp)
+    a.detach_optimizer()
+    a.step()
+    torch.cuda.synchronize()
+    with pytest.raises(L.ConnectorError):
+        a.train_step()
