@@ -650,15 +650,16 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ------------------------------------------------------------------ the trainer step (clip + AdamW) beside it (needs the engine's peer
+    # bucket, which the strong-scaling block and the e2e leg close: one peer / multicast bucket at a time)
+    trainer = None
+    if not args.no_extras:
+        trainer = trainer_leg(torch, dist, eng, max(20, min(args.steps, 200)), world)
+
     # ------------------------------------------------------------------ strong scaling (BASELINE configs[4]) beside it
     strong = None
     if world > 1 and not args.global_batch and args.config == "cfg2" and not args.no_extras and 256 % world == 0:
         strong = strong_scaling_block(torch, dist, pkg, w, dev, rank, world, eng, ms_per_step, args)
-
-    # ------------------------------------------------------------------ the trainer step (clip + AdamW) beside it
-    trainer = None
-    if not args.no_extras:
-        trainer = trainer_leg(torch, dist, eng, max(20, min(args.steps, 200)), world)
 
     # ------------------------------------------------------------------ end to end from pinned host tensors
     e2e = None
