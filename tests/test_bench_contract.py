@@ -37,8 +37,9 @@ class FakeEngine:
         self.K = 6144
         self.bias_in_gemm = True
         self.status = torch.zeros(1, dtype=torch.int32)
-        peer = types.SimpleNamespace(mc=FakeEngine.mc, check=lambda: None, close=lambda: None) \
-            if self.fused_allreduce else None
+        peer = types.SimpleNamespace(mc=FakeEngine.mc, check=lambda: None, closed=False) if self.fused_allreduce else None
+        if peer is not None:
+            peer.close = lambda: setattr(peer, "closed", True)
         self.bucket = types.SimpleNamespace(peer=peer)
         self.launches_per_step = 5 if self.direct else 7
         self.events = None
@@ -60,6 +61,12 @@ class FakeEngine:
         return 4 * self.M * 4096
 
 
+def fake_trainer_leg(torch_, dist_, eng, steps, world):
+    # the leg all-reduces through the engine's own peer bucket: it has to run before anything closes that bucket
+    assert eng.bucket.peer is None or not eng.bucket.peer.closed, "trainer leg after the peer bucket was closed"
+    return {"ms_per_step": 120.0, "value": 1.5}
+
+
 def run_bench(argv, world, fused, mc):
     import audio_visual_llm_b200.engine as E
     import bench
@@ -79,7 +86,7 @@ def run_bench(argv, world, fused, mc):
     with mock.patch.dict("os.environ", env), mock.patch.object(sys, "argv", ["bench.py"] + argv), \
             mock.patch.object(E, "ConnectorStep", FakeEngine), mock.patch("torch.cuda.set_device"), \
             mock.patch.object(bench, "self_check", lambda *a, **k: dict(fake_check)), \
-            mock.patch.object(bench, "trainer_leg", lambda *a, **k: {"ms_per_step": 120.0, "value": 1.5}), \
+            mock.patch.object(bench, "trainer_leg", fake_trainer_leg), \
             mock.patch.object(bench, "graphed_leg", lambda *a, **k: {"ms_per_step": 50.0, "value": 2.0}), \
             mock.patch.object(bench, "gpu_eager_leg", lambda *a, **k: dict(fake_eager, cublas=dict(fake_eager["cublas"]))), \
             mock.patch("torch.cuda.Event", FakeEvent), mock.patch("torch.cuda.synchronize"), \
