@@ -81,8 +81,26 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.fast, self._fast_stop = [], threading.Event()   # NVML samples every ~2 ms: (time, sm MHz, reason bits)
+
+    def _nvml_loop(self):
+        """The same counters straight from NVML every ~2 ms, so that the driver-sized 17 ms region holds more than one
+        sample; nvidia-smi (20 ms) stays the record when NVML is unavailable."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._fast_stop.is_set():
+                self.fast.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons(h))))
+                time.sleep(0.002)
+        except Exception:
+            return
 
     def start(self):
+        threading.Thread(target=self._nvml_loop, daemon=True).start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -104,6 +122,7 @@ class ClockSampler:
             time.sleep(0.01)
 
     def stop(self):
+        self._fast_stop.set()
         if self.proc is None:
             return
         self.proc.terminate()
@@ -134,8 +153,24 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "window": window}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+               "samples": len(sm), "window": window}
+        fast = [f for f in list(self.fast) if t0 <= f[0] <= t1]
+        if len(fast) >= 3:
+            # NVML reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown
+            bits = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+            clk = sorted(f[1] for f in fast)
+            seen = set()
+            for f in fast:
+                seen |= {n for b, n in bits.items() if f[2] & b}
+            out["nvml"] = {"sm_mhz": clk[len(clk) // 2], "sm_mhz_min": clk[0], "samples": len(clk),
+                           "reasons": sorted(seen)}
+            if window != "timed region" or len(sm) < 3:
+                # too few nvidia-smi lines inside a short region: the NVML samples ARE inside it
+                out.update(sm_mhz=clk[len(clk) // 2], reasons=sorted(set(out["reasons"]) | seen if window == "timed region"
+                                                                      else seen),
+                           samples=len(clk), window="timed region (NVML, 2 ms period)")
+        return out
 
 
 def reference_arm(args, rank: int):
