@@ -123,6 +123,22 @@ def main():
     report("tn_gemm_dw_shape_f32out", lambda: L.proj_fwd([At], [Wt], Yt), flops=2 * M * K * H)
     del At, Wt, Yt
     report("colsum", lambda: L.colsum(dY, db, None, ws), nbytes=M * H * 2)
+    # train-time length adaptation of the reference (clip_whisper_model.py:621-707) at the cfg2' size:
+    # [32, 16 + 1500, 4096] -> [32, 256, 4096] adaptive average pool, and its backward
+    from audio_visual_llm_b200 import seq_adapt
+    Sx, Lt = P + Ta, 256
+    xs = torch.randn(B, Sx, H, device=dev).to(torch.bfloat16)
+    ys = torch.empty(B, Lt, H, dtype=torch.bfloat16, device=dev)
+    dxs = torch.empty_like(xs)
+    fwd_t, bwd_t = seq_adapt._device_taps(Sx, Lt, dev)
+    report("resample_pool_fwd", lambda: L.row_resample(xs, ys, *fwd_t), nbytes=(xs.numel() + ys.numel()) * 2)
+    report("resample_pool_bwd", lambda: L.row_resample(ys, dxs, *bwd_t), nbytes=(xs.numel() + ys.numel()) * 2)
+    xs2 = torch.randn(B, 116, H, device=dev).to(torch.bfloat16)   # 16 + 100 video frames -> 256 (linear interpolation)
+    f2, b2 = seq_adapt._device_taps(116, Lt, dev)
+    dxs2 = torch.empty_like(xs2)
+    report("resample_interp_fwd", lambda: L.row_resample(xs2, ys, *f2), nbytes=(xs2.numel() + ys.numel()) * 2)
+    report("resample_interp_bwd", lambda: L.row_resample(ys, dxs2, *b2), nbytes=(xs2.numel() + ys.numel()) * 2)
+    del xs, dxs, xs2, dxs2
     report("torch_matmul_fwd", lambda: torch.matmul(A, W.t(), out=Y), flops=2 * M * K * H)
     dWb = torch.empty(H, K, dtype=torch.bfloat16, device=dev)
     report("torch_matmul_dw", lambda: torch.matmul(dY.t(), A, out=dWb), flops=2 * M * K * H)
