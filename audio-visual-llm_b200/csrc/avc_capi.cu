@@ -93,6 +93,31 @@ int make_map3d(CUtensorMap* map, const void* ptr, int elem, int64_t cols, int64_
   if (batches == 1) batch_stride_elems = rows * row_stride_elems;
   if ((batch_stride_elems * es) % 16 != 0)
     return fail(AVC_ERR_INVALID, "%s: batch stride must be a multiple of 16 bytes", what);
+  // Encoded maps are a pure function of (pointer, element type, extents, strides, box): a small per-thread
+  // direct-mapped cache spares the driver call when a caller comes back with the same buffers (decode loops, the
+  // static-buffer step engine).  SURVEY.md 8(b): "no global state beyond cached TMA descriptors".
+  struct Key {
+    const void* ptr;
+    int64_t cols, rows, batches, rs, bs;
+    int elem, box_cols, box_rows;
+    bool operator==(const Key& o) const {
+      return ptr == o.ptr && cols == o.cols && rows == o.rows && batches == o.batches && rs == o.rs && bs == o.bs &&
+             elem == o.elem && box_cols == o.box_cols && box_rows == o.box_rows;
+    }
+  };
+  struct Slot { Key key; CUtensorMap map; bool used; };
+  constexpr int kSlots = 64;
+  thread_local Slot slots[kSlots] = {};
+  const Key key{ptr, cols, rows, batches, row_stride_elems, batch_stride_elems, elem, box_cols, box_rows};
+  uint64_t hsh = reinterpret_cast<uintptr_t>(ptr) >> 4;
+  hsh = (hsh ^ static_cast<uint64_t>(cols) * 0x9E3779B97F4A7C15ull ^ static_cast<uint64_t>(rows) * 0xC2B2AE3D27D4EB4Full ^
+         static_cast<uint64_t>(box_cols) * 0x165667B19E3779F9ull ^ static_cast<uint64_t>(box_rows) * 0x27D4EB2F165667C5ull ^
+         static_cast<uint64_t>(batches) * 0x85EBCA77C2B2AE63ull) * 0xD6E8FEB86659FD93ull;
+  Slot& slot = slots[(hsh >> 32) % kSlots];
+  if (slot.used && slot.key == key) {
+    *map = slot.map;
+    return AVC_OK;
+  }
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(batches)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems * es),
@@ -108,6 +133,9 @@ int make_map3d(CUtensorMap* map, const void* ptr, int elem, int64_t cols, int64_
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(AVC_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, static_cast<int>(r));
+  slot.key = key;
+  slot.map = *map;
+  slot.used = true;
   return AVC_OK;
 }
 
