@@ -12,7 +12,6 @@ fp16 here as well: bf16 tensor-core operands, fp32 accumulate, fp16 pack in the 
 """
 from __future__ import annotations
 
-import logging
 
 import torch
 import torch.nn as nn
