@@ -704,7 +704,6 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
 #pragma unroll
                 for (int i = 0; i < RB; ++i) acc4[i][0] = acc4[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int row0 = tile_row0 + h * BM + r0;
-#pragma unroll 1
                 // unconditional loads (rows / columns past the edge re-read the last valid one and are dropped at the
                 // store): nothing keeps the compiler from issuing the 16 loads of a slice back to back
                 int roff[RB], coff[2];
@@ -717,6 +716,7 @@ __global__ void __launch_bounds__(threads_for(COMM != 0), 1) gemm_kernel(const _
                   if (out_col0 + c4 >= ncols) c4 = ncols - out_col0 - 4;
                   coff[j] = c4;
                 }
+#pragma unroll 1
                 for (int s2 = 0; s2 < ksplit; ++s2) {
                   const float* ps = wsb + static_cast<int64_t>(s2) * args.ws_split_stride;
                   float4 t[RB][2];
