@@ -114,7 +114,7 @@ def drive(m, d, cfg, dev, train):
     return m.llm.calls[-1]
 
 
-@pytest.mark.parametrize("llm_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("llm_dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("name", CASES)
 def test_model_forward_backward_matches_executing_reference(avc, cuda_dev, name, llm_dtype):
     d, cfg = load(name)
