@@ -35,6 +35,17 @@ CASES = {
     # training branch: adaptive avg-pool to the label length / linear interpolation up to it
     "train_pool": dict(modality="both", Ta=24, Tv=12, fs=0.5, max_seq_len=512, P=4, L=10, train=True),
     "train_interp": dict(modality="both", Ta=8, Tv=6, fs=0.5, max_seq_len=512, P=0, L=19, train=True),
+    # round 2: more of the reference's branches
+    # video only with a prompt, training branch: 5 + 10 rows interpolated up to 30 label positions
+    "train_video_only_prompt": dict(modality="video", Ta=None, Tv=10, fs=0.5, max_seq_len=256, P=5, L=30, train=True),
+    # audio only, training branch: 40 rows pooled down to 12
+    "train_audio_only_pool": dict(modality="audio", Ta=40, Tv=None, fs=0.5, max_seq_len=256, P=0, L=12, train=True),
+    # fusion_scale 1.0 (the video projection is multiplied by 0), labels exactly as long as the sequence
+    "both_equal_len_fs1": dict(modality="both", Ta=16, Tv=16, fs=1.0, max_seq_len=256, P=2, L=18, train=False),
+    # fusion_scale 0.0, fused length exactly at the cap
+    "both_fs0_cap_exact": dict(modality="both", Ta=16, Tv=16, fs=0.0, max_seq_len=16, P=0, L=16, train=False),
+    # training branch with labels as long as the sequence: no length adaptation
+    "train_same_len": dict(modality="both", Ta=12, Tv=6, fs=0.4, max_seq_len=512, P=4, L=16, train=True),
 }
 B, DA, DV, H, VOCAB, PAD, NP = 2, 32, 16, 48, 64, 0, 3
 
