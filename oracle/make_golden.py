@@ -118,6 +118,34 @@ def cfg1():
     return rec
 
 
+def adaptive_connector():
+    """The reference's `adaptive` connector type (modality_connector.py:239-382) built by its own factory, eval mode:
+    weights, one short input (attention block only) and one longer than 512 frames (two stride-2 convolutions first),
+    outputs and the gradients of both dense projections for a fixed upstream gradient."""
+    mc, _ = R.load_reference_modules()
+    torch.manual_seed(11)
+    conn = mc.create_modality_connector("adaptive", 32, 48, device="cpu", dtype=torch.float32, max_seq_len=640).eval()
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():  # the factory zero-initialises every bias: give them values so that they are exercised
+        for n, p in conn.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    x = torch.randn(2, 40, 32, generator=g)
+    x_long = torch.randn(1, 520, 32, generator=g)
+    up = torch.randn(2, 40, 48, generator=g)
+    y = conn(x)
+    (y * up).sum().backward()
+    rec = {f"sd.{k}": v.detach().numpy() for k, v in conn.state_dict().items()}
+    rec.update({"in.x": x.numpy(), "in.x_long": x_long.numpy(), "in.upstream": up.numpy(), "out.y": y.detach().numpy(),
+                "out.input_proj.weight.grad": conn.input_proj.weight.grad.numpy(),
+                "out.input_proj.bias.grad": conn.input_proj.bias.grad.numpy(),
+                "out.output_proj.weight.grad": conn.output_proj.weight.grad.numpy(),
+                "out.output_proj.bias.grad": conn.output_proj.bias.grad.numpy()})
+    with torch.no_grad():
+        rec["out.y_long"] = conn(x_long).numpy()
+    return rec
+
+
 def main():
     if not R.available():
         raise SystemExit("/root/reference is not mounted: goldens can only be generated in the build container")
@@ -127,6 +155,8 @@ def main():
         print("wrote", name)
     np.savez_compressed(GOLDEN / "ref_cfg1_subsampled.npz", **cfg1())
     print("wrote cfg1")
+    np.savez_compressed(GOLDEN / "adaptive_connector.npz", **adaptive_connector())
+    print("wrote adaptive connector")
 
 
 if __name__ == "__main__":

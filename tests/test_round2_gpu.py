@@ -672,3 +672,31 @@ def test_graphed_encoder_replays_the_eager_bits(avc, cuda_dev):
         torch.cuda.synchronize()
         assert torch.equal(gemb, emb) and torch.equal(gmask, mask), trial
     assert len(graphed._graphs) == 1, "one capture serves every call with the same input signature"
+
+
+def test_adaptive_connector_matches_the_executing_reference(avc, cuda_dev):
+    """tests/golden/adaptive_connector.npz: the reference's own `adaptive` connector (its factory, eval mode) -- weights,
+    inputs, outputs and the gradients of its two dense projections.  Our module must load that state dict as is and
+    reproduce the outputs (bf16 tensor-core operands, fp32 accumulate: REL_TOL) for a short input and for one longer
+    than 512 frames (the two stride-2 convolutions)."""
+    import numpy as np
+    from pathlib import Path
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "adaptive_connector.npz")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    conn = avc.create_modality_connector("adaptive", 32, 48, device="cuda:0", max_seq_len=640).eval()
+    missing = conn.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    x = torch.from_numpy(z["in.x"]).to(cuda_dev)
+    up = torch.from_numpy(z["in.upstream"]).to(cuda_dev)
+    y = conn(x)
+    (y * up).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(y, torch.from_numpy(z["out.y"]), "adaptive forward vs reference", rel=2e-2)
+    for name in ("input_proj", "output_proj"):
+        lin = getattr(conn, name)
+        assert_close(lin.weight.grad, torch.from_numpy(z[f"out.{name}.weight.grad"]), f"{name} dW vs reference", rel=3e-2)
+        assert_close(lin.bias.grad, torch.from_numpy(z[f"out.{name}.bias.grad"]), f"{name} db vs reference", rel=3e-2)
+    with torch.no_grad():
+        y_long = conn(torch.from_numpy(z["in.x_long"]).to(cuda_dev))
+    assert_close(y_long, torch.from_numpy(z["out.y_long"]), "adaptive forward, 520 frames", rel=2e-2)
